@@ -1,0 +1,228 @@
+/* pbsed_b200.h -- C ABI of libpbsed_b200.so (hand-written sm_100a kernels for the
+ * pb_sed FBCRNN / BiCRNN hot path).
+ *
+ * Conventions:
+ *   - every entry point returns 0 on success, a negative PBSED_E* code for a bad
+ *     argument, or a positive cudaError_t for a launch failure; nothing throws;
+ *   - nothing allocates, frees or synchronises: the caller owns every buffer and
+ *     passes the cudaStream_t (as void*) the work is enqueued on;
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - activations are fp32 "rows x channels" matrices, rows = (b, f, t) in that
+ *     order, channels contiguous:  2-D maps (B,F,T,C), 1-D maps (B,T,C) (F = 1).
+ *     The reference's (B,C,F,T) log-mel with C = 1 is the same memory as (B,F,T,1).
+ *   - seq_len (int32[B], nullable = all frames valid) carries the reference's
+ *     sequence-length masking (padertorch Normalization / Mean / pack_padded).
+ *
+ * Each function names the reference interface it replaces; pb_sed paths are
+ * relative to /root/reference, third-party ones are padertorch@b7ba24a /
+ * paderbox@809b272 (pinned in README.md:40-41; source not vendored).
+ */
+#ifndef PBSED_B200_H
+#define PBSED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBSED_EINVAL   (-1)   /* bad argument / unsupported shape            */
+#define PBSED_EWORKSPACE (-2) /* workspace too small                         */
+#define PBSED_MAX_TAPS 16
+
+/* library identification: returns the ABI version (bumped on signature change) */
+int pbsed_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long pbsed_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  STFT -> |.|^2 -> mel -> log      (replaces paderbox stft as configured at
+ *     pb_sed/data_preparation/provider.py:315-323 and called at
+ *     pb_sed/data_preparation/transform.py:53, plus MelTransform inside
+ *     NormalizedLogMelExtractor, call site pb_sed/models/weak_label/crnn.py:86-90)
+ *
+ * audio (B, S) fp32 -> logmel (B, n_mels, T) fp32 = log(mel_power + 1e-18).
+ * fading='half' zero padding, pad=True tail, periodic Blackman window of
+ * `window_length`, zero padded to `fft_size` (power of two, <= 2048).
+ * window:  (window_length) fp32.   fbank_lo/fbank_hi: int32[n_mels] first/last+1
+ * fft bin of each triangular filter, fbank_w: (n_mels, fbank_stride) fp32 weights
+ * for bins lo..hi-1 (row-normalised HTK-mel triangles).
+ * stats (nullable): double[n_mels][2], accumulates sum / sum-of-squares of logmel
+ * over valid frames (t < seq_len[b]) for the cumulative running normalisation.
+ */
+int pbsed_stft_logmel(const float* audio, int B, int S,
+                      int shift, int window_length, int fft_size, int pad_front, int T,
+                      const float* window,
+                      const int* fbank_lo, const int* fbank_hi, const float* fbank_w,
+                      int fbank_stride, int n_mels,
+                      const int* seq_len, float* logmel, double* stats, void* stream);
+
+/* power spectrogram input variant (reference-compatible 5-D `stft` input,
+ * (B, T, n_bins, 2) fp32 re/im):  same outputs as above. */
+int pbsed_spec_logmel(const float* stft, int B, int T, int n_bins,
+                      const int* fbank_lo, const int* fbank_hi, const float* fbank_w,
+                      int fbank_stride, int n_mels,
+                      const int* seq_len, float* logmel, double* stats, void* stream);
+
+/* normalise + clamp + mask in place:  x = clamp(x * scale[f] + shift[f], +-clamp) * (t < seq_len[b])
+ * with scale = rsqrt(var+eps), shift = -mean*scale from pbsed_norm_finalize
+ * (padertorch Normalization('bcft', statistics_axis='bt', no affine) + clamp(+-6)) */
+int pbsed_logmel_normalize(float* x, int B, int F, int T, const float* scale, const float* shift,
+                           float clamp, const int* seq_len, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  tap-GEMM: the one contraction behind CNN2d / CNN1d / GRU projections / output_net
+ *     (replaces padertorch.contrib.je.modules.conv.{CNN2d,CNN1d} layer bodies,
+ *     configured at pb_sed/experiments/weak_label_crnn/training.py:218-242, and the
+ *     nn.GRU input projection / output_net 1x1 convs, training.py:243-260)
+ *
+ *   out[(b,fo,t), n] = bias[n] + sum_tap sum_c  a[(b, fo+df[tap], t+dt[tap]), c] * W[tap][n][c]
+ *   a[(b,f,t), c]    = act( in[(b,f,t), c] * scale[.] + shift[.] )  if 0<=f<F_in, 0<=t<T, t<seq_len[b]
+ *                    = 0 otherwise   ('same' zero padding happens AFTER norm+ReLU: pre-activation)
+ *   scale/shift index = c (per_f == 0) or f*Cin + c (per_f == 1); scale == NULL -> identity.
+ *   relu != 0 -> act = max(.,0).
+ *   W layout: [ntaps][w_tap_stride] with element (n, c) at n*w_sn + c*w_sc  (so forward uses
+ *   w_sn = Cin, w_sc = 1 and the data-gradient pass reuses the same weights transposed with
+ *   w_sn = 1, w_sc = Cout_fwd and negated taps).
+ *   epilogue (nullable extras):
+ *     out_mul_relu_of: if given (same shape as out) with ep_scale/ep_shift, multiplies the
+ *       result by [ (v*ep_scale+ep_shift) > 0 ] * (t < seq_len[b])  -- the ReLU/mask backward of a
+ *       pre-activation layer when this call is a data-gradient pass.
+ */
+typedef struct {
+  int B, F_in, F_out, T;
+  int Cin, Cout;
+  int ntaps;
+  int df[PBSED_MAX_TAPS];
+  int dt[PBSED_MAX_TAPS];
+  int relu;          /* ReLU on the loaded operand               */
+  int per_f;         /* scale/shift (and ep_*) indexed by f*C + c */
+  long long w_tap_stride, w_sn, w_sc;
+  int in_stride;     /* row stride of `in` in floats  (0 -> Cin;  lets a GRU direction read its half of a (B,T,2H) map) */
+  int out_stride;    /* row stride of `out` / `dout` / `ep_src` in floats (0 -> Cout) */
+  int precision;     /* 0 = exact fp32 FFMA; 1 = 3xTF32 tcgen05; 2 = bf16 tcgen05 (where supported) */
+} pbsed_tapgemm_desc;
+
+int pbsed_tapgemm(const pbsed_tapgemm_desc* d_host,
+                  const float* in, const float* scale, const float* shift, const int* seq_len,
+                  const float* W, const float* bias, float* out,
+                  const float* ep_src, const float* ep_scale, const float* ep_shift,
+                  void* stream);
+
+/* weight gradient of the same contraction:
+ *   dW[tap][n][c] += sum_{b,fo,t}  dout[(b,fo,t), n] * a[(b, fo+df, t+dt), c]       (a as above)
+ *   dbias[n]      += sum_{b,fo,t}  dout[(b,fo,t), n]                                (nullable)
+ * dW uses the forward layout (w_sn = Cin, w_sc = 1).  ACCUMULATES: caller zeroes the gradient arena.
+ * rows with t >= seq_len[b] of dout are ignored when mask_out != 0. */
+int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d_host,
+                        const float* in, const float* scale, const float* shift, const int* seq_len,
+                        const float* dout, int mask_out, float* dW, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Normalisation / pooling helpers (padertorch Normalization + max_pool2d)
+ */
+/* stats[idx][0..1] += sum, sum of squares over valid rows; idx = c or f*C+c (per_f). double[.][2] */
+int pbsed_channel_stats(const float* x, int B, int F, int T, int C, int per_f,
+                        const int* seq_len, double* stats, void* stream);
+/* batch statistics -> affine used on load, and running-statistics update.
+ *   n = count (valid rows per channel), mean = s/n, var = ss/n - mean^2 (biased)
+ *   scale = gamma * rsqrt(var+eps); shift = beta - mean*scale; save_mean/save_rstd for backward.
+ *   momentum >= 0: running = momentum*running + (1-momentum)*batch    (CNN layers, 0.95)
+ *   momentum <  0: cumulative average over num_tracked (feature-extractor norm)
+ *   training == 0: scale/shift from running statistics, nothing updated.
+ *   cumulative (momentum<0) & training: scale/shift from the UPDATED running stats
+ *   (interpolation_factor = 1), var unbiased n/(n-1) as padertorch does for momentum None. */
+int pbsed_norm_finalize(const double* stats, double count, int nch,
+                        const float* gamma, const float* beta, float eps, float momentum, int training,
+                        float* running_mean, float* running_power, float* num_tracked,
+                        float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
+/* frequency max-pool by `pool` (rows (B,F,T,C) -> (B,F/pool,T,C)); idx (uint8) = argmax offset */
+int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool,
+                    float* y, uint8_t* idx, void* stream);
+int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C, int pool,
+                        float* dx, void* stream);
+/* batch-norm backward, two passes.  g = gradient w.r.t. the normalised+affine output (already
+ * multiplied by the ReLU mask), x = the layer input the statistics were taken on.
+ *   pass 1: sums[idx][0] += sum g ; sums[idx][1] += sum g * xhat       (valid rows only)
+ *   pass 2: dx = gamma*rstd * ( g - sums0/n - xhat * sums1/n ) ; dgamma += sums1 ; dbeta += sums0
+ *           rows t >= seq_len[b] get dx = 0.  dx may alias g. */
+int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int F, int T, int C, int per_f,
+                          const int* seq_len, const float* save_mean, const float* save_rstd,
+                          double* sums, void* stream);
+int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F, int T, int C, int per_f,
+                         const int* seq_len, const float* save_mean, const float* save_rstd,
+                         const float* gamma, const double* sums, double count,
+                         float* dx, float* dgamma, float* dbeta, void* stream);
+/* out = [add +] x  with the tag condition broadcast (B,K) -> extra channels; see pbsed_concat_cond */
+/* rows (B,F,T,C) <- concat( x (B,F,T,C0), cond (B,K) broadcast over f,t )  (strong_label/crnn.py:86-91) */
+int pbsed_concat_cond(const float* x, const float* cond, int B, int F, int T, int C0, int K,
+                      float* out, void* stream);
+/* dx (B,F,T,C0) <- dout[..., :C0]  (cond carries no gradient) */
+int pbsed_split_cond_bwd(const float* dout, int B, int F, int T, int C0, int K, float* dx, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  GRU recurrence   (replaces torch.nn.GRU inside padertorch.contrib.je.modules.rnn.GRU,
+ *     call sites pb_sed/models/weak_label/crnn.py:62,66 and strong_label/crnn.py:92)
+ *
+ * One launch runs `ndir` independent directions of ONE layer.  Direction d uses
+ *   gi   + d*gi_dir_stride   : (B,T,3H) input projection x@W_ih^T + b_ih  (gate order r,z,n)
+ *   w_hh + d*3H*H            : (3H,H),   b_hh + d*3H : (3H)
+ *   reverse[d] != 0          : time runs seq_len[b]-1 .. 0 (the reference's reverse=True /
+ *                              the backward direction of bidirectional=True)
+ *   h_out + d*h_dir_off      : (B,T,h_stride) rows, writes H channels (zeros at t >= seq_len[b])
+ *   save + d*B*T*4H          : (B,T,4H) = r, z, n, (W_hn h + b_hn)  for backward (nullable)
+ * H must be a multiple of 32 and <= 256 (one thread-block cluster of H/32 CTAs per 8-clip batch
+ * slice and direction, W_hh resident in registers); h0 = 0.
+ */
+int pbsed_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh, const float* b_hh,
+                  const int* seq_len, int B, int T, int H, int ndir, const int* reverse_host,
+                  float* h_out, long long h_dir_off, int h_stride, float* save, void* stream);
+/* backward through time.  dh_out: gradient w.r.t. h_out (same addressing as h_out).
+ * writes dgi (B,T,3H per dir, stride gi_dir_stride) = dL/d(gi) = [dr, dz, dn] and
+ * dgh (same addressing) = dL/d(W_hh h + b_hh) = [dr, dz, dn*r]; zeros at t >= seq_len[b].
+ * The weight gradients are then plain tap-GEMM wgrads (dW_ih: dgi x input, dW_hh: dgh x h_out
+ * shifted one step against the direction of time, dt = -1 / +1 with seq_len masking). */
+int pbsed_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride,
+                  const float* h_out, const float* save, const float* w_hh,
+                  const int* seq_len, int B, int T, int H, int ndir, const int* reverse_host,
+                  float* dgi, float* dgh, long long gi_dir_stride, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  scores + losses
+ *     bounded sigmoid (pb_sed/models/weak_label/crnn.py:58-59; min_score = 0 -> nn.Sigmoid of
+ *     strong_label/crnn.py:93) with the (B,T,K) -> (B,K,T) transpose the model API returns.
+ */
+int pbsed_sigmoid_btk_to_bkt(const float* z, int B, int T, int K, float min_score, float* y, void* stream);
+/* dz (B,T,K) = dy (B,K,T) * (1-2*min) * s(1-s), s = sigmoid(z) */
+int pbsed_sigmoid_bwd(const float* dy, const float* z, int B, int T, int K, float min_score,
+                      float* dz, void* stream);
+/* FBCRNN review loss, forward + backward in one pass
+ *   (pb_sed/models/weak_label/crnn.py:107-153,180-206).
+ * y_fwd, y_bwd (B,K,T) scores (y_bwd nullable), weak (B,K), boundary (B,K,T) (nullable when
+ * strong_weight == 0), class_weights (K, nullable).
+ * out_host-free: loss_out[0] = loss, loss_out[1] = sum of weights; dy_* (nullable) gradients.
+ * workspace: float[2*B*K + 8]. */
+int pbsed_fbcrnn_loss(const float* y_fwd, const float* y_bwd, const float* weak, const float* boundary,
+                      const float* class_weights, const int* seq_len, int B, int K, int T,
+                      float strong_weight, float label_smoothing,
+                      float* loss_out, float* dy_fwd, float* dy_bwd, float* workspace, void* stream);
+/* BiCRNN review loss (pb_sed/models/strong_label/crnn.py:107-112) */
+int pbsed_bicrnn_loss(const float* y, const float* strong, const int* seq_len, int B, int K, int T,
+                      float* loss_out, float* dy, float* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K5  gradient-norm clip + Adam over one flat arena
+ *     (replaces padertorch.train.optimizer.Adam = clip_grad_norm_ + torch.optim.Adam,
+ *     configured at pb_sed/experiments/weak_label_crnn/training.py:264-269)
+ * hyper (device float[8]): lr, beta1, beta2, eps, max_norm, step (incremented here), grad_scale, -
+ * sumsq (device double[1]) is zeroed by step 1 of the NEXT call (the caller zeroes it once).
+ * grad_norm_out (device float[1]) receives the pre-clip global L2 norm.
+ */
+int pbsed_grad_sumsq(const float* g, long long n, const float* hyper, double* sumsq, void* stream);
+int pbsed_adam_step(float* p, float* g, float* m, float* v, long long n, float* hyper,
+                    double* sumsq, float* grad_norm_out, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBSED_B200_H */

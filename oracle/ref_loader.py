@@ -1,0 +1,102 @@
+"""Load the REAL pb_sed model classes from /root/reference on top of the oracle shims.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Only usable in the build
+container (``/root/reference`` does not exist on the GPU box); used by
+``tests/golden/make_golden.py`` to pin the pb_sed-owned arithmetic
+(``CRNN.forward/review/sigmoid`` and the inference heads) and by the optional
+``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
+
+pb_sed imports ``padertorch`` / ``paderbox`` (absent here).  We register stub
+modules under those names that expose the restatements from
+``oracle/pt_port.py`` and then exec the reference source files *unmodified*:
+
+    pb_sed/models/base/model.py          (SoundEventModel)
+    pb_sed/models/weak_label/crnn.py     (FBCRNN)
+    pb_sed/models/strong_label/crnn.py   (tag-conditioned BiCRNN)
+    pb_sed/evaluation/instance_based.py  (numpy only)
+
+``pb_sed.models.base.__init__`` also imports the inference / tuning drivers
+(sed_scores_eval, sacred ...), which are out of scope, so that package is
+stubbed with just ``SoundEventModel``.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+from . import pt_port
+
+REFERENCE_ROOT = os.environ.get('PB_SED_REFERENCE', '/root/reference')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'pb_sed', 'models', 'weak_label', 'crnn.py'))
+
+
+def _stub(name, **attrs):
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+def _exec(name, relpath):
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def segment_axis(x, length, shift, axis=-1, end='cut'):
+    """paderbox.array.segment_axis for the one call pattern pb_sed uses
+    (strong_label/crnn.py:126-131: length == shift, axis=0, end='cut')."""
+    x = np.asarray(x)
+    axis = axis % x.ndim
+    n = (x.shape[axis] - length) // shift + 1
+    idx = np.arange(n)[:, None] * shift + np.arange(length)[None, :]
+    return np.take(x, idx, axis=axis)
+
+
+_loaded = {}
+
+
+def load():
+    """returns (weak_label_crnn_module, strong_label_crnn_module)."""
+    if _loaded:
+        return _loaded['weak'], _loaded['strong']
+    assert reference_available(), REFERENCE_ROOT
+    if not hasattr(np, 'int'):       # pb_sed uses the removed alias (weak_label/crnn.py:252)
+        np.int = int
+    P = pt_port
+    _stub('padertorch', Model=P.Model)
+    _stub('padertorch.ops')
+    _stub('padertorch.ops.sequence')
+    _stub('padertorch.ops.sequence.mask', compute_mask=P.compute_mask)
+    _stub('padertorch.contrib')
+    _stub('padertorch.contrib.je')
+    _stub('padertorch.contrib.je.modules')
+    _stub('padertorch.contrib.je.modules.conv', Pad=P.Pad, CNN1d=P.CNN1d, CNN2d=P.CNN2d)
+    _stub('padertorch.contrib.je.modules.hybrid', CNN=P.CNN)
+    _stub('padertorch.contrib.je.modules.features',
+          NormalizedLogMelExtractor=P.NormalizedLogMelExtractor)
+    _stub('padertorch.contrib.je.modules.reduce',
+          TakeLast=P.TakeLast, Mean=P.Mean, Sum=P.Sum, Max=P.Max)
+    _stub('padertorch.contrib.je.modules.rnn', GRU=P.GRU, TransformerEncoder=None)
+    _stub('paderbox')
+    _stub('paderbox.array', segment_axis=segment_axis)
+    _stub('pb_sed')
+    _stub('pb_sed.evaluation')
+    inst = _exec('pb_sed.evaluation.instance_based', 'pb_sed/evaluation/instance_based.py')
+    sys.modules['pb_sed.evaluation'].instance_based = inst
+    _stub('pb_sed.models')
+    model_mod = _exec('pb_sed.models.base.model', 'pb_sed/models/base/model.py')
+    base = _stub('pb_sed.models.base', SoundEventModel=model_mod.SoundEventModel)
+    sys.modules['pb_sed.models'].base = base
+    weak = _exec('pb_sed.models.weak_label.crnn', 'pb_sed/models/weak_label/crnn.py')
+    strong = _exec('pb_sed.models.strong_label.crnn', 'pb_sed/models/strong_label/crnn.py')
+    _loaded.update(weak=weak, strong=strong)
+    return weak, strong

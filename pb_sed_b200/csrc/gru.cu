@@ -1,0 +1,307 @@
+// gru.cu -- persistent, register-resident GRU recurrence (forward and BPTT) for sm_100a.
+//
+// Reference: torch.nn.GRU inside padertorch.contrib.je.modules.rnn.GRU, called at
+// pb_sed/models/weak_label/crnn.py:62,66 (rnn_fwd / rnn_bwd = same config + reverse=True,
+// :338-340) and pb_sed/models/strong_label/crnn.py:92 (bidirectional=True); gate order r,z,n:
+//     r = s(gi_r + W_hr h + b_hr)   z = s(gi_z + W_hz h + b_hz)
+//     n = tanh(gi_n + r * (W_hn h + b_hn))     h' = (1-z) n + z h
+// packed-sequence semantics: clip b only advances for its seq_len[b] valid frames; the
+// reverse direction walks t = len-1 .. 0; outputs at padded frames are zero.
+//
+// Mapping: one thread-block CLUSTER of NC = H/32 CTAs per (direction, 8-clip batch slice).
+// CTA `rank` owns hidden units [32*rank, 32*rank+32).  Thread (warp q, lane j) keeps the
+// W_hh entries {gate g} x {unit u = 32*rank + j} x {k in [q*H/8, (q+1)*H/8)} in REGISTERS
+// for the whole sequence (3*H/8 = 96 registers at H = 256), so the 500 dependent steps never
+// re-read the weights.  Per step: h_{t-1} (8 x H, replicated in every CTA's shared memory)
+// is multiplied against the register tile, the 8 k-slices are reduced through shared memory,
+// the gate math runs on thread (q = clip, j = unit), and the new h is pushed to every CTA of
+// the cluster through distributed shared memory, followed by one cluster barrier.
+#include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+struct GruDirs { int reverse[4]; };
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int H>
+__global__ void __launch_bounds__(256, 1)
+gru_fwd_kernel(const float* __restrict__ gi, long long gi_dir_stride, const float* __restrict__ w_hh,
+               const float* __restrict__ b_hh, const int* __restrict__ seq_len, int B, int T,
+               GruDirs dirs, float* __restrict__ h_out, long long h_dir_off, int h_stride,
+               float* __restrict__ save) {
+  constexpr int NC = H / 32, KS = H / 8, BC = 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, q = tid >> 5, j = tid & 31;
+  const int u = rank * 32 + j;
+  const int d = blockIdx.z;
+  const bool reverse = dirs.reverse[d] != 0;
+  const int bq = blockIdx.y * BC + q;
+
+  __shared__ __align__(16) float hbuf[2][BC][H];
+  __shared__ float red[8][3][BC][32];
+
+  const float* w = w_hh + (long long)d * 3 * H * H;
+  const float* bh = b_hh + (long long)d * 3 * H;
+  float W[3][KS];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) W[g][kk] = __ldg(w + (long long)(g * H + u) * H + q * KS + kk);
+  const float bhr = __ldg(bh + u), bhz = __ldg(bh + H + u), bhn = __ldg(bh + 2 * H + u);
+
+  for (int i = tid; i < 2 * BC * H; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+  const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
+  const float* gi_b = gi + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
+  float* ho_b = h_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
+  float* sv_b = save ? save + ((long long)d * B + bq) * T * 4 * H : nullptr;
+  float hprev = 0.f;
+  cluster.sync();
+
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1;
+    const bool active = s < len;
+    const int t = reverse ? (len - 1 - s) : s;
+    float gir = 0.f, giz = 0.f, gin = 0.f;
+    if (active) {
+      const float* p = gi_b + (long long)t * 3 * H + u;
+      gir = __ldg(p); giz = __ldg(p + H); gin = __ldg(p + 2 * H);
+    }
+    float acc[3][BC];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int b = 0; b < BC; ++b) acc[g][b] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS; kk += 4) {
+#pragma unroll
+      for (int b = 0; b < BC; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][b][q * KS + kk]);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          acc[g][b] = fmaf(W[g][kk], hv.x, acc[g][b]);
+          acc[g][b] = fmaf(W[g][kk + 1], hv.y, acc[g][b]);
+          acc[g][b] = fmaf(W[g][kk + 2], hv.z, acc[g][b]);
+          acc[g][b] = fmaf(W[g][kk + 3], hv.w, acc[g][b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int b = 0; b < BC; ++b) red[q][g][b][j] = acc[g][b];
+    __syncthreads();
+    float ghr = bhr, ghz = bhz, ghn = bhn;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      ghr += red[qq][0][q][j]; ghz += red[qq][1][q][j]; ghn += red[qq][2][q][j];
+    }
+    float hnew = hprev;
+    if (active) {
+      const float r = sigmoidf_(gir + ghr);
+      const float z = sigmoidf_(giz + ghz);
+      const float n = tanhf(fmaf(r, ghn, gin));
+      hnew = (1.f - z) * n + z * hprev;
+      ho_b[(long long)t * h_stride + u] = hnew;
+      if (sv_b) {
+        float* sp = sv_b + (long long)t * 4 * H + u;
+        sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = ghn;
+      }
+    } else if (bq < B) {
+      ho_b[(long long)s * h_stride + u] = 0.f;       // padded frame t = s >= len
+    }
+    hprev = hnew;
+    float* mine = &hbuf[cur ^ 1][q][u];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) *cluster.map_shared_rank(mine, c) = hnew;
+    cluster.sync();
+  }
+}
+
+// ------------------------------------------------------------------ BPTT
+template <int H>
+__global__ void __launch_bounds__(256, 1)
+gru_bwd_kernel(const float* __restrict__ dh_out, long long h_dir_off, int h_stride,
+               const float* __restrict__ h_out, const float* __restrict__ save,
+               const float* __restrict__ w_hh, const int* __restrict__ seq_len, int B, int T,
+               GruDirs dirs, float* __restrict__ dgi, float* __restrict__ dgh,
+               long long gi_dir_stride) {
+  constexpr int NC = H / 32, KS = H / 8, BC = 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, q = tid >> 5, j = tid & 31;
+  const int u = rank * 32 + j;
+  const int d = blockIdx.z;
+  const bool reverse = dirs.reverse[d] != 0;
+  const int bq = blockIdx.y * BC + q;
+
+  extern __shared__ __align__(16) float smem[];
+  float* dg = smem;                            // [2][3][BC][H]
+  float* red = smem + 2 * 3 * BC * H;          // [8][BC][32]
+
+  const float* w = w_hh + (long long)d * 3 * H * H;
+  float Wt[3][KS];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) Wt[g][kk] = __ldg(w + (long long)(g * H + q * KS + kk) * H + u);
+
+  const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
+  const float* dho_b = dh_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
+  const float* ho_b = h_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
+  const float* sv_b = save + ((long long)d * B + bq) * T * 4 * H;
+  float* dgi_b = dgi + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
+  float* dgh_b = dgh + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
+  float dh_carry = 0.f;
+  cluster.sync();
+
+  for (int s = T - 1; s >= 0; --s) {
+    const int cur = s & 1;
+    const bool active = s < len;
+    const int t = reverse ? (len - 1 - s) : s;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, direct = dh_carry;
+    if (active) {
+      const float dh = dh_carry + __ldg(dho_b + (long long)t * h_stride + u);
+      const float* sp = sv_b + (long long)t * 4 * H + u;
+      const float r = __ldg(sp), z = __ldg(sp + H), n = __ldg(sp + 2 * H), ghn = __ldg(sp + 3 * H);
+      float hp = 0.f;
+      if (s > 0) hp = __ldg(ho_b + (long long)(reverse ? t + 1 : t - 1) * h_stride + u);
+      const float dn = dh * (1.f - z) * (1.f - n * n);
+      const float dz = dh * (hp - n) * z * (1.f - z);
+      const float dr = dn * ghn * r * (1.f - r);
+      v0 = dr; v1 = dz; v2 = dn * r;
+      float* gp = dgi_b + (long long)t * 3 * H + u;
+      gp[0] = dr; gp[H] = dz; gp[2 * H] = dn;
+      float* hp2 = dgh_b + (long long)t * 3 * H + u;
+      hp2[0] = dr; hp2[H] = dz; hp2[2 * H] = v2;
+      direct = dh * z;
+    } else if (bq < B) {
+      float* gp = dgi_b + (long long)s * 3 * H + u;
+      gp[0] = 0.f; gp[H] = 0.f; gp[2 * H] = 0.f;
+      float* hp2 = dgh_b + (long long)s * 3 * H + u;
+      hp2[0] = 0.f; hp2[H] = 0.f; hp2[2 * H] = 0.f;
+    }
+    float* m0 = dg + ((cur * 3 + 0) * BC + q) * H + u;
+    float* m1 = dg + ((cur * 3 + 1) * BC + q) * H + u;
+    float* m2 = dg + ((cur * 3 + 2) * BC + q) * H + u;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      *cluster.map_shared_rank(m0, c) = v0;
+      *cluster.map_shared_rank(m1, c) = v1;
+      *cluster.map_shared_rank(m2, c) = v2;
+    }
+    cluster.sync();
+    float acc[BC];
+#pragma unroll
+    for (int b = 0; b < BC; ++b) acc[b] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int kk = 0; kk < KS; kk += 4)
+#pragma unroll
+        for (int b = 0; b < BC; ++b) {
+          const float4 dv = *reinterpret_cast<const float4*>(dg + ((cur * 3 + g) * BC + b) * H + q * KS + kk);
+          acc[b] = fmaf(Wt[g][kk], dv.x, acc[b]);
+          acc[b] = fmaf(Wt[g][kk + 1], dv.y, acc[b]);
+          acc[b] = fmaf(Wt[g][kk + 2], dv.z, acc[b]);
+          acc[b] = fmaf(Wt[g][kk + 3], dv.w, acc[b]);
+        }
+#pragma unroll
+    for (int b = 0; b < BC; ++b) red[(q * BC + b) * 32 + j] = acc[b];
+    __syncthreads();
+    float sum = direct;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) sum += red[(qq * BC + q) * 32 + j];
+    dh_carry = sum;
+  }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int H>
+static int launch_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh,
+                          const float* b_hh, const int* seq_len, int B, int T, int ndir,
+                          const GruDirs& dirs, float* h_out, long long h_dir_off, int h_stride,
+                          float* save, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H / 32, cdiv(B, 8), ndir);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_fwd_kernel<H>, gi, gi_dir_stride, w_hh, b_hh, seq_len,
+                                     B, T, dirs, h_out, h_dir_off, h_stride, save);
+  ++g_pbsed_launches;
+  if (e != cudaSuccess) return (int)e;
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int H>
+static int launch_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride, const float* h_out,
+                          const float* save, const float* w_hh, const int* seq_len, int B, int T,
+                          int ndir, const GruDirs& dirs, float* dgi, float* dgh,
+                          long long gi_dir_stride, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * 3 * 8 * H + 8 * 8 * 32) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H / 32, cdiv(B, 8), ndir);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gru_bwd_kernel<H>, dh_out, h_dir_off, h_stride, h_out, save, w_hh,
+                         seq_len, B, T, dirs, dgi, dgh, gi_dir_stride);
+  ++g_pbsed_launches;
+  if (e != cudaSuccess) return (int)e;
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+static int make_dirs(int ndir, const int* reverse_host, GruDirs& dirs) {
+  if (ndir < 1 || ndir > 4 || !reverse_host) return PBSED_EINVAL;
+  for (int i = 0; i < 4; ++i) dirs.reverse[i] = i < ndir ? reverse_host[i] : 0;
+  return 0;
+}
+
+extern "C" int pbsed_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh,
+                             const float* b_hh, const int* seq_len, int B, int T, int H, int ndir,
+                             const int* reverse_host, float* h_out, long long h_dir_off,
+                             int h_stride, float* save, void* stream) {
+  GruDirs dirs;
+  if (make_dirs(ndir, reverse_host, dirs)) return PBSED_EINVAL;
+  if (!gi || !w_hh || !b_hh || !h_out || B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (H) {
+    case 32:  return launch_gru_fwd<32>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
+    case 64:  return launch_gru_fwd<64>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
+    case 128: return launch_gru_fwd<128>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
+    case 256: return launch_gru_fwd<256>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
+    default:  return PBSED_EINVAL;
+  }
+}
+
+extern "C" int pbsed_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride,
+                             const float* h_out, const float* save, const float* w_hh,
+                             const int* seq_len, int B, int T, int H, int ndir,
+                             const int* reverse_host, float* dgi, float* dgh,
+                             long long gi_dir_stride, void* stream) {
+  GruDirs dirs;
+  if (make_dirs(ndir, reverse_host, dirs)) return PBSED_EINVAL;
+  if (!dh_out || !h_out || !save || !w_hh || !dgi || !dgh || B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (H) {
+    case 32:  return launch_gru_bwd<32>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
+    case 64:  return launch_gru_bwd<64>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
+    case 128: return launch_gru_bwd<128>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
+    case 256: return launch_gru_bwd<256>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
+    default:  return PBSED_EINVAL;
+  }
+}

@@ -1,0 +1,317 @@
+// norm_pool.cu -- masked batch statistics, running-statistics update, frequency max-pool and
+// their backward passes.
+//
+// Reference semantics (padertorch.contrib.je.modules.norm.Normalization as used
+// with norm='batch', norm_kwargs={'eps': 1e-3} at pb_sed/experiments/weak_label_crnn/training.py:
+// 224-225,236-237,255-256): statistics over (b, f, t) per channel [2-D] / (b, t) per feature [1-D],
+// masked by seq_len along t, biased variance, momentum 0.95 running mean / running power,
+// learnable scale/shift; padded frames are zeroed.  F.max_pool2d((2,1)) after the conv.
+#include "common.cuh"
+
+// ------------------------------------------------------------------ channel statistics
+// generic two-quantity column reduction over valid rows:
+//   MODE 0: (x, x^2)            MODE 1: (g, g * (x - mean) * rstd)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const float* __restrict__ a, const float* __restrict__ x, int F, int T, int C,
+                 int per_f, const int* __restrict__ seq_len, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, double* __restrict__ out, int t_chunk) {
+  __shared__ float red[2][256];
+  const int tid = threadIdx.x;
+  const int g = blockIdx.x;                     // (b, f) row group
+  const int b = g / F, f = g % F;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+  const int t0 = blockIdx.y * t_chunk;
+  const int t1 = min(t0 + t_chunk, len_b);
+  if (t0 >= t1) return;                          // uniform per CTA
+  const long long row0 = (long long)g * T;
+  const int Cw = C < 256 ? C : 256;
+  const int rl = 256 / Cw;                       // row lanes
+  const int lane_r = tid / Cw, c_local = tid % Cw;
+  const bool active = lane_r < rl;
+  const int idx_base = per_f ? f * C : 0;
+  for (int c = c_local; c < C; c += Cw) {        // >1 trip only when C > 256 (then rl == 1)
+    float s0 = 0.f, s1 = 0.f;
+    if (active) {
+      float mu = 0.f, rs = 1.f;
+      if (MODE == 1) { mu = __ldg(mean + idx_base + c); rs = __ldg(rstd + idx_base + c); }
+      for (int t = t0 + lane_r; t < t1; t += rl) {
+        const long long o = (row0 + t) * C + c;
+        if (MODE == 0) {
+          const float v = __ldg(a + o);
+          s0 += v; s1 = fmaf(v, v, s1);
+        } else {
+          const float gv = __ldg(a + o);
+          const float xh = (__ldg(x + o) - mu) * rs;
+          s0 += gv; s1 = fmaf(gv, xh, s1);
+        }
+      }
+    }
+    if (rl == 1) {
+      atomicAdd(out + 2 * (idx_base + c), (double)s0);
+      atomicAdd(out + 2 * (idx_base + c) + 1, (double)s1);
+    } else {
+      red[0][tid] = s0; red[1][tid] = s1;
+      __syncthreads();
+      if (lane_r == 0) {
+        double d0 = 0., d1 = 0.;
+        for (int r = 0; r < rl; ++r) { d0 += (double)red[0][r * Cw + c_local]; d1 += (double)red[1][r * Cw + c_local]; }
+        atomicAdd(out + 2 * (idx_base + c), d0);
+        atomicAdd(out + 2 * (idx_base + c) + 1, d1);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static int stats_t_chunk(int B, int F, int T) {
+  // enough CTAs to fill 148 SMs a few times over, chunks of >= 32 frames
+  long long groups = (long long)B * F;
+  int chunks = (int)((148LL * 8 + groups - 1) / groups);
+  if (chunks < 1) chunks = 1;
+  int tc = (T + chunks - 1) / chunks;
+  if (tc < 32) tc = 32;
+  return tc;
+}
+
+extern "C" int pbsed_channel_stats(const float* x, int B, int F, int T, int C, int per_f,
+                                   const int* seq_len, double* stats, void* stream) {
+  if (!x || !stats || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
+  const int tc = stats_t_chunk(B, F, T);
+  dim3 grid(B * F, cdiv(T, tc));
+  colreduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
+                                                              nullptr, nullptr, stats, tc);
+  return pbsed_after_launch();
+}
+
+extern "C" int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int F, int T, int C,
+                                     int per_f, const int* seq_len, const float* save_mean,
+                                     const float* save_rstd, double* sums, void* stream) {
+  if (!g || !x || !sums || !save_mean || !save_rstd || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
+  const int tc = stats_t_chunk(B, F, T);
+  dim3 grid(B * F, cdiv(T, tc));
+  colreduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
+                                                              save_mean, save_rstd, sums, tc);
+  return pbsed_after_launch();
+}
+
+// ------------------------------------------------------------------ finalize
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, double count, int nch,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float eps, float momentum, int training,
+                                     float* __restrict__ running_mean, float* __restrict__ running_power,
+                                     float* __restrict__ num_tracked, float* __restrict__ scale,
+                                     float* __restrict__ shift, float* __restrict__ save_mean,
+                                     float* __restrict__ save_rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nch) return;
+  const float ga = gamma ? gamma[i] : 1.f;
+  const float be = beta ? beta[i] : 0.f;
+  float mu, var;
+  if (training) {
+    const double m = stats[2 * i] / count;
+    double v = stats[2 * i + 1] / count - m * m;
+    if (v < 0.) v = 0.;
+    mu = (float)m; var = (float)v;
+    const float power = (float)(v + m * m);
+    if (save_mean) { save_mean[i] = mu; save_rstd[i] = rsqrtf(var + eps); }
+    if (running_mean) {
+      if (momentum >= 0.f) {
+        running_mean[i] = momentum * running_mean[i] + (1.f - momentum) * mu;
+        running_power[i] = momentum * running_power[i] + (1.f - momentum) * power;
+        num_tracked[i] += (float)count;
+      } else {
+        const float n = (float)count;
+        const float tot = num_tracked[i] + n;
+        const float rm = running_mean[i] + (mu - running_mean[i]) * n / tot;
+        const float rp = running_power[i] + (power - running_power[i]) * n / tot;
+        running_mean[i] = rm; running_power[i] = rp; num_tracked[i] = tot;
+        // interpolation_factor = 1: normalise with the updated cumulative statistics
+        mu = rm;
+        var = (rp - rm * rm) * tot / fmaxf(tot - 1.f, 1.f);
+      }
+    }
+  } else {
+    mu = running_mean[i];
+    var = running_power[i] - mu * mu;
+    if (momentum < 0.f) {
+      const float n = num_tracked[i];
+      var = var * n / fmaxf(n - 1.f, 1.f);
+    }
+  }
+  const float sc = ga / sqrtf(var + eps);
+  scale[i] = sc;
+  shift[i] = be - mu * sc;
+}
+
+extern "C" int pbsed_norm_finalize(const double* stats, double count, int nch, const float* gamma,
+                                   const float* beta, float eps, float momentum, int training,
+                                   float* running_mean, float* running_power, float* num_tracked,
+                                   float* scale, float* shift, float* save_mean, float* save_rstd,
+                                   void* stream) {
+  if (nch < 1 || !scale || !shift) return PBSED_EINVAL;
+  if (training && (!stats || count <= 0.)) return PBSED_EINVAL;
+  if (!training && (!running_mean || !running_power)) return PBSED_EINVAL;
+  if (running_mean && (!running_power || !num_tracked)) return PBSED_EINVAL;
+  norm_finalize_kernel<<<cdiv(nch, 128), 128, 0, (cudaStream_t)stream>>>(
+      stats, count, nch, gamma, beta, eps, momentum, training, running_mean, running_power,
+      num_tracked, scale, shift, save_mean, save_rstd);
+  return pbsed_after_launch();
+}
+
+// ------------------------------------------------------------------ norm backward apply
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, int F, int T, int C,
+                      int per_f, const int* __restrict__ seq_len, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                      const double* __restrict__ sums, float inv_n, float* __restrict__ dx,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long total,
+                      int nch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    const long long row = i / C;
+    const int t = (int)(row % T);
+    const long long gq = row / T;
+    const int f = (int)(gq % F), b = (int)(gq / F);
+    const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+    float r = 0.f;
+    if (t < len_b) {
+      const int idx = (per_f ? f * C : 0) + c;
+      const float rs = __ldg(rstd + idx);
+      const float xh = (__ldg(x + i) - __ldg(mean + idx)) * rs;
+      const float s0 = (float)sums[2 * idx] * inv_n, s1 = (float)sums[2 * idx + 1] * inv_n;
+      const float ga = gamma ? __ldg(gamma + idx) : 1.f;
+      r = ga * rs * (__ldg(g + i) - s0 - xh * s1);
+    }
+    dx[i] = r;
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int j = threadIdx.x; j < nch; j += blockDim.x) {
+      dbeta[j] += (float)sums[2 * j];
+      dgamma[j] += (float)sums[2 * j + 1];
+    }
+  }
+}
+
+extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F, int T, int C,
+                                    int per_f, const int* seq_len, const float* save_mean,
+                                    const float* save_rstd, const float* gamma, const double* sums,
+                                    double count, float* dx, float* dgamma, float* dbeta,
+                                    void* stream) {
+  if (!g || !x || !sums || !dx || !save_mean || !save_rstd || count <= 0.) return PBSED_EINVAL;
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return PBSED_EINVAL;
+  const long long total = (long long)B * F * T * C;
+  const int nch = per_f ? F * C : C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  norm_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      g, x, F, T, C, per_f, seq_len, save_mean, save_rstd, gamma, sums, (float)(1.0 / count), dx,
+      dgamma, dbeta, total, nch);
+  return pbsed_after_launch();
+}
+
+// ------------------------------------------------------------------ frequency max-pool
+__global__ void __launch_bounds__(256)
+maxpool_f_kernel(const float* __restrict__ x, int F, long long TC, int pool, float* __restrict__ y,
+                 uint8_t* __restrict__ idx, long long total_out) {
+  const int Fo = F / pool;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_out; i += stride) {
+    const long long tc = i % TC;
+    const long long gq = i / TC;
+    const int fo = (int)(gq % Fo);
+    const long long b = gq / Fo;
+    const float* src = x + ((b * F + (long long)fo * pool) * TC + tc);
+    float best = __ldg(src);
+    int bi = 0;
+    for (int k = 1; k < pool; ++k) {
+      const float v = __ldg(src + (long long)k * TC);
+      if (v > best || (v != v)) { best = v; bi = k; }     // first max wins, NaN propagates (ATen)
+    }
+    y[i] = best;
+    if (idx) idx[i] = (uint8_t)bi;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_f_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, int F,
+                     long long TC, int pool, float* __restrict__ dx, long long total_in) {
+  const int Fo = F / pool;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_in; i += stride) {
+    const long long tc = i % TC;
+    const long long gq = i / TC;
+    const int f = (int)(gq % F);
+    const long long b = gq / F;
+    const int fo = f / pool;
+    float v = 0.f;
+    if (fo < Fo) {
+      const long long o = (b * Fo + fo) * TC + tc;
+      if ((int)idx[o] == f - fo * pool) v = __ldg(dy + o);
+    }
+    dx[i] = v;
+  }
+}
+
+static int ew_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool, float* y,
+                               uint8_t* idx, void* stream) {
+  if (!x || !y || pool < 1 || pool > 255 || F / pool < 1) return PBSED_EINVAL;
+  const long long total = (long long)B * (F / pool) * T * C;
+  maxpool_f_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, F, (long long)T * C, pool, y, idx, total);
+  return pbsed_after_launch();
+}
+
+extern "C" int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C,
+                                   int pool, float* dx, void* stream) {
+  if (!dy || !idx || !dx || pool < 1 || F / pool < 1) return PBSED_EINVAL;
+  const long long total = (long long)B * F * T * C;
+  maxpool_f_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, idx, F, (long long)T * C, pool, dx, total);
+  return pbsed_after_launch();
+}
+
+// ------------------------------------------------------------------ tag-condition concat
+__global__ void __launch_bounds__(256)
+concat_cond_kernel(const float* __restrict__ x, const float* __restrict__ cond, long long FT, int C0,
+                   int K, float* __restrict__ out, long long total) {
+  const int C = C0 + K;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    const long long row = i / C;
+    const long long b = row / FT;
+    out[i] = c < C0 ? __ldg(x + row * C0 + c) : __ldg(cond + b * K + (c - C0));
+  }
+}
+__global__ void __launch_bounds__(256)
+split_cond_bwd_kernel(const float* __restrict__ dout, int C0, int K, float* __restrict__ dx,
+                      long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C0);
+    const long long row = i / C0;
+    dx[i] = __ldg(dout + row * (C0 + K) + c);
+  }
+}
+
+extern "C" int pbsed_concat_cond(const float* x, const float* cond, int B, int F, int T, int C0,
+                                 int K, float* out, void* stream) {
+  if (!x || !cond || !out || C0 < 1 || K < 1) return PBSED_EINVAL;
+  const long long total = (long long)B * F * T * (C0 + K);
+  concat_cond_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, cond, (long long)F * T, C0, K, out, total);
+  return pbsed_after_launch();
+}
+extern "C" int pbsed_split_cond_bwd(const float* dout, int B, int F, int T, int C0, int K, float* dx,
+                                    void* stream) {
+  if (!dout || !dx || C0 < 1 || K < 1) return PBSED_EINVAL;
+  const long long total = (long long)B * F * T * C0;
+  split_cond_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dout, C0, K, dx, total);
+  return pbsed_after_launch();
+}

@@ -1,0 +1,449 @@
+"""Thin torch-facing wrappers + autograd Functions over the C ABI (``include/pbsed_b200.h``).
+
+Device memory and streams come from torch; all arithmetic happens in the hand-written
+sm_100a kernels of ``libpbsed_b200.so``.  There is no eager / CPU fallback: every function
+asserts CUDA tensors and calls through ``_lib.call``.
+
+Native activation layout ("rows x channels"): 2-D maps ``(B, F, T, C)``, 1-D maps
+``(B, T, C)``; channels contiguous.  The reference's ``(B, C, F, T)`` / ``(B, C, T)`` tensors
+are exposed as permuted *views* of these (``to_native`` / ``from_native`` are zero-copy when
+the tensor was produced by this package).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TapGemmDesc, call
+
+PRECISION = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
+_default_precision = 0
+
+
+def set_default_precision(p):
+    """'fp32' (exact FFMA), 'tf32x3' (tcgen05 split-TF32), 'bf16' (tcgen05) for the tap-GEMMs."""
+    global _default_precision
+    _default_precision = PRECISION[p] if isinstance(p, str) else int(p)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, 'pb_sed_b200 ops run on CUDA tensors only (no CPU fallback)'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------ sequence lengths
+class SeqLen:
+    """host + device copy of the per-clip number of valid frames (None == all valid)."""
+    _cache = {}
+
+    def __init__(self, host, T, device):
+        self.host = host                      # np.int64 array or None
+        self.T = T
+        self.dev = None
+        if host is not None:
+            self.dev = torch.from_numpy(np.minimum(host, T).astype(np.int32)).to(device)
+
+    @classmethod
+    def make(cls, seq_len, B, T, device):
+        if isinstance(seq_len, SeqLen):
+            assert seq_len.T == T, (seq_len.T, T)
+            return seq_len
+        if seq_len is None:
+            key = (None, B, T, str(device))
+        else:
+            host = np.asarray(seq_len).astype(np.int64).reshape(-1)
+            assert host.shape[0] == B, (host.shape, B)
+            if (host >= T).all():
+                host = None                   # nothing to mask: skip the predicate everywhere
+                key = (None, B, T, str(device))
+            else:
+                key = (host.tobytes(), B, T, str(device))
+        s = cls._cache.get(key)
+        if s is None:
+            if len(cls._cache) > 256:
+                cls._cache.clear()
+            s = cls(None if key[0] is None else host, T, device)
+            s.B = B
+            cls._cache[key] = s
+        return s
+
+    @property
+    def ptr(self):
+        return _ptr(self.dev)
+
+    def frames(self):
+        """total number of valid frames over the batch."""
+        return float(self.B * self.T) if self.host is None else float(np.minimum(self.host, self.T).sum())
+
+
+def to_native(x):
+    """(B,C,F,T) -> (B,F,T,C) / (B,C,T) -> (B,T,C), contiguous (zero-copy for our own views)."""
+    if x.dim() == 4:
+        return x.permute(0, 2, 3, 1).contiguous()
+    return x.transpose(1, 2).contiguous()
+
+
+def from_native(x):
+    if x.dim() == 4:
+        return x.permute(0, 3, 1, 2)
+    return x.transpose(1, 2)
+
+
+# ------------------------------------------------------------------ raw kernels
+def make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=False, per_f=False, transpose_w=False,
+              in_stride=0, out_stride=0, precision=None):
+    d = TapGemmDesc()
+    d.B, d.F_in, d.F_out, d.T, d.Cin, d.Cout = B, F_in, F_out, T, Cin, Cout
+    d.ntaps = len(taps)
+    assert 1 <= d.ntaps <= _lib.MAX_TAPS, d.ntaps
+    for i, (df, dt) in enumerate(taps):
+        d.df[i], d.dt[i] = int(df), int(dt)
+    d.relu, d.per_f = int(relu), int(per_f)
+    d.w_tap_stride = Cin * Cout
+    if transpose_w:          # this call's (Cout, Cin) are the forward layer's (Cin, Cout)
+        d.w_sn, d.w_sc = 1, Cout
+    else:
+        d.w_sn, d.w_sc = Cin, 1
+    d.in_stride, d.out_stride = in_stride, out_stride
+    d.precision = _default_precision if precision is None else precision
+    return d
+
+
+def tapgemm(x, W, bias, desc, scale=None, shift=None, seq=None, ep_src=None, ep_scale=None,
+            ep_shift=None, out=None, x_ptr=None):
+    rows = desc.B * desc.F_out * desc.T
+    if out is None:
+        out = torch.empty((rows, desc.Cout), device=W.device, dtype=torch.float32)
+    call('pbsed_tapgemm', ctypes.byref(desc), x_ptr if x_ptr is not None else _ptr(x), _ptr(scale),
+         _ptr(shift), seq.ptr if seq is not None else None, _ptr(W), _ptr(bias), _ptr(out),
+         _ptr(ep_src), _ptr(ep_scale), _ptr(ep_shift), _stream())
+    return out
+
+
+def tapgemm_wgrad(x, dout, desc, dW, dbias, scale=None, shift=None, seq=None, mask_out=True,
+                  x_ptr=None, dout_ptr=None, dW_ptr=None, dbias_ptr=None):
+    call('pbsed_tapgemm_wgrad', ctypes.byref(desc), x_ptr if x_ptr is not None else _ptr(x),
+         _ptr(scale), _ptr(shift), seq.ptr if seq is not None else None,
+         dout_ptr if dout_ptr is not None else _ptr(dout), int(mask_out),
+         dW_ptr if dW_ptr is not None else _ptr(dW),
+         dbias_ptr if dbias_ptr is not None else _ptr(dbias), _stream())
+
+
+def _grad_target(p):
+    """accumulate straight into ``p.grad`` when it exists (flat-arena training), else into a
+    fresh zero buffer that is returned to autograd."""
+    if p is None or not p.requires_grad:
+        return None, None
+    if p.grad is not None:
+        return p.grad, None
+    g = torch.zeros_like(p)
+    return g, g
+
+
+# ------------------------------------------------------------------ conv layer
+class ConvLayerFn(torch.autograd.Function):
+    """[norm -> ReLU ->] zero-pad -> tap-conv(+bias) [-> frequency max-pool] on native maps.
+
+    x: (B, F_in, T, Cin) native.  weight: (ntaps, Cout, Cin).  Returns (B, F_out', T, Cout).
+    cfg: dict(F_in, F_out, taps, relu, per_f, pool, eps, momentum, training, norm: bool)
+    norm buffers (running_mean, running_power, num_tracked) are updated in place.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, rmean, rpower, ntracked, seq, cfg):
+        x = _f32c(x)
+        B, F_in, T, Cin = x.shape
+        ntaps, Cout, Cin_w = weight.shape
+        assert Cin_w == Cin and F_in == cfg['F_in'], (weight.shape, x.shape, cfg)
+        F_out, pool = cfg['F_out'], cfg.get('pool', 1)
+        per_f = cfg.get('per_f', False)
+        scale = shift = smean = srstd = None
+        nch = (F_in if per_f else 1) * Cin
+        count = seq.frames() * (1 if per_f else F_in)
+        if cfg['norm']:
+            scale = torch.empty(nch, device=x.device)
+            shift = torch.empty(nch, device=x.device)
+            if cfg['training']:
+                stats = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
+                call('pbsed_channel_stats', _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                     _ptr(stats), _stream())
+                smean = torch.empty(nch, device=x.device)
+                srstd = torch.empty(nch, device=x.device)
+                call('pbsed_norm_finalize', _ptr(stats), count, nch, _ptr(gamma), _ptr(beta),
+                     cfg['eps'], cfg['momentum'], 1, _ptr(rmean), _ptr(rpower), _ptr(ntracked),
+                     _ptr(scale), _ptr(shift), _ptr(smean), _ptr(srstd), _stream())
+            else:
+                call('pbsed_norm_finalize', None, 1.0, nch, _ptr(gamma), _ptr(beta), cfg['eps'],
+                     cfg['momentum'], 0, _ptr(rmean), _ptr(rpower), _ptr(ntracked), _ptr(scale),
+                     _ptr(shift), None, None, _stream())
+        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f)
+        z = tapgemm(x, weight, bias, desc, scale, shift, seq).view(B, F_out, T, Cout)
+        idx = None
+        if pool > 1:
+            y = torch.empty((B, F_out // pool, T, Cout), device=x.device)
+            idx = torch.empty(y.shape, device=x.device, dtype=torch.uint8)
+            call('pbsed_maxpool_f', _ptr(z), B, F_out, T, Cout, pool, _ptr(y), _ptr(idx), _stream())
+        else:
+            y = z
+        ctx.cfg, ctx.seq, ctx.count = cfg, seq, count
+        ctx.save_for_backward(x, weight, gamma, scale, shift, smean, srstd, idx)
+        ctx.params = (weight, bias, gamma, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, gamma, scale, shift, smean, srstd, idx = ctx.saved_tensors
+        w_p, b_p, g_p, be_p = ctx.params
+        cfg, seq = ctx.cfg, ctx.seq
+        B, F_in, T, Cin = x.shape
+        ntaps, Cout, _ = weight.shape
+        F_out, pool, per_f = cfg['F_out'], cfg.get('pool', 1), cfg.get('per_f', False)
+        dy = _f32c(dy)
+        if pool > 1:
+            dz = torch.empty((B, F_out, T, Cout), device=x.device)
+            call('pbsed_maxpool_f_bwd', _ptr(dy), _ptr(idx), B, F_out, T, Cout, pool, _ptr(dz), _stream())
+        else:
+            dz = dy
+        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f)
+        dW, dW_ret = _grad_target(w_p)
+        db, db_ret = _grad_target(b_p)
+        if dW is not None:
+            tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq, mask_out=False)
+        dx = dg_ret = dbe_ret = None
+        if ctx.needs_input_grad[0]:
+            rtaps = [(-df, -dt) for df, dt in cfg['taps']]
+            ddesc = make_desc(B, F_out, F_in, T, Cout, Cin, rtaps, per_f=per_f, transpose_w=True)
+            use_ep = cfg['relu'] or cfg['norm']
+            g = tapgemm(dz, weight, None, ddesc, None, None, seq,
+                        ep_src=x if use_ep and cfg['relu'] else None,
+                        ep_scale=scale if cfg['relu'] else None,
+                        ep_shift=shift if cfg['relu'] else None).view(B, F_in, T, Cin)
+            if cfg['norm'] and cfg['training']:
+                nch = (F_in if per_f else 1) * Cin
+                sums = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
+                call('pbsed_norm_bwd_reduce', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                     _ptr(smean), _ptr(srstd), _ptr(sums), _stream())
+                dga, dg_ret = _grad_target(g_p)
+                dbe, dbe_ret = _grad_target(be_p)
+                call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                     _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), ctx.count, _ptr(g),
+                     _ptr(dga), _ptr(dbe), _stream())
+                dx = g
+            elif cfg['norm']:
+                # eval-mode norm is a fixed affine: dx = g * scale  (rare: frozen-stat finetuning)
+                sc = scale.view(F_in, 1, Cin) if per_f else scale
+                dx = g * sc
+            else:
+                dx = g
+        return dx, dW_ret, db_ret, dg_ret, dbe_ret, None, None, None, None, None
+
+
+# ------------------------------------------------------------------ GRU layer
+class GruLayerFn(torch.autograd.Function):
+    """one GRU layer, ``ndir`` directions.  x (B,T,In) native; weights stacked per direction:
+    w_ih (ndir,3H,In), w_hh (ndir,3H,H), b_ih/b_hh (ndir,3H).  Returns (B,T,ndir*H)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, seq, reverse):
+        x = _f32c(x)
+        B, T, In = x.shape
+        ndir, H3, H = w_hh.shape
+        gi = torch.empty((ndir, B, T, H3), device=x.device)
+        for d in range(ndir):
+            desc = make_desc(B, 1, 1, T, In, H3, [(0, 0)])
+            tapgemm(x, w_ih[d], b_ih[d], desc, seq=seq, out=gi[d])
+        h = torch.empty((B, T, ndir * H), device=x.device)
+        save = torch.empty((ndir, B, T, 4 * H), device=x.device)
+        rev = (ctypes.c_int * 4)(*([int(r) for r in reverse] + [0] * (4 - ndir)))
+        call('pbsed_gru_fwd', _ptr(gi), B * T * H3, _ptr(w_hh), _ptr(b_hh), seq.ptr, B, T, H, ndir,
+             rev, _ptr(h), H, ndir * H, _ptr(save), _stream())
+        ctx.seq, ctx.reverse = seq, list(reverse)
+        ctx.save_for_backward(x, w_ih, w_hh, h, save)
+        ctx.params = (w_ih, w_hh, b_ih, b_hh)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, w_ih, w_hh, h, save = ctx.saved_tensors
+        p_wih, p_whh, p_bih, p_bhh = ctx.params
+        seq, reverse = ctx.seq, ctx.reverse
+        B, T, In = x.shape
+        ndir, H3, H = w_hh.shape
+        dh = _f32c(dh)
+        dgi = torch.empty((ndir, B, T, H3), device=x.device)
+        dgh = torch.empty((ndir, B, T, H3), device=x.device)
+        rev = (ctypes.c_int * 4)(*([int(r) for r in reverse] + [0] * (4 - ndir)))
+        call('pbsed_gru_bwd', _ptr(dh), H, ndir * H, _ptr(h), _ptr(save), _ptr(w_hh), seq.ptr, B, T,
+             H, ndir, rev, _ptr(dgi), _ptr(dgh), B * T * H3, _stream())
+        dwih, r0 = _grad_target(p_wih)
+        dwhh, r1 = _grad_target(p_whh)
+        dbih, r2 = _grad_target(p_bih)
+        dbhh, r3 = _grad_target(p_bhh)
+        dx = None
+        for d in range(ndir):
+            if dwih is not None:
+                desc = make_desc(B, 1, 1, T, In, H3, [(0, 0)])
+                tapgemm_wgrad(x, dgi[d], desc, dwih[d], dbih[d] if dbih is not None else None,
+                              seq=seq, mask_out=True)
+            if dwhh is not None:
+                desc = make_desc(B, 1, 1, T, H, H3, [(0, 1 if reverse[d] else -1)], in_stride=ndir * H)
+                tapgemm_wgrad(None, dgh[d], desc, dwhh[d], dbhh[d] if dbhh is not None else None,
+                              seq=seq, mask_out=True,
+                              x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * d * H))
+            if ctx.needs_input_grad[0]:
+                ddesc = make_desc(B, 1, 1, T, H3, In, [(0, 0)], transpose_w=True)
+                g = tapgemm(dgi[d], w_ih[d], None, ddesc, seq=seq).view(B, T, In)
+                dx = g if dx is None else dx.add_(g)
+        return dx, r0, r1, r2, r3, None, None
+
+
+# ------------------------------------------------------------------ misc element-wise ops
+class ConcatCondFn(torch.autograd.Function):
+    """native rows (B,F,T,C0) ++ cond (B,K) broadcast -> (B,F,T,C0+K)  (strong_label/crnn.py:86-91)."""
+
+    @staticmethod
+    def forward(ctx, x, cond):
+        x = _f32c(x)
+        cond = _f32c(cond)
+        shp = x.shape
+        B, C0 = shp[0], shp[-1]
+        FT = int(np.prod(shp[1:-1]))
+        K = cond.shape[1]
+        out = torch.empty(shp[:-1] + (C0 + K,), device=x.device)
+        call('pbsed_concat_cond', _ptr(x), _ptr(cond), B, 1, FT, C0, K, _ptr(out), _stream())
+        ctx.dims = (B, FT, C0, K, shp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, FT, C0, K, shp = ctx.dims
+        dx = torch.empty(shp, device=dout.device)
+        call('pbsed_split_cond_bwd', _ptr(_f32c(dout)), B, 1, FT, C0, K, _ptr(dx), _stream())
+        return dx, None
+
+
+class SigmoidScoresFn(torch.autograd.Function):
+    """logits (B,T,K) native -> scores (B,K,T) = min + (1 - 2 min) * sigmoid (weak_label/crnn.py:58-59)."""
+
+    @staticmethod
+    def forward(ctx, z, min_score):
+        z = _f32c(z)
+        B, T, K = z.shape
+        y = torch.empty((B, K, T), device=z.device)
+        call('pbsed_sigmoid_btk_to_bkt', _ptr(z), B, T, K, float(min_score), _ptr(y), _stream())
+        ctx.save_for_backward(z)
+        ctx.min_score = float(min_score)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, = ctx.saved_tensors
+        B, T, K = z.shape
+        dz = torch.empty_like(z)
+        call('pbsed_sigmoid_bwd', _ptr(_f32c(dy)), _ptr(z), B, T, K, ctx.min_score, _ptr(dz), _stream())
+        return dz, None
+
+
+class FbcrnnLossFn(torch.autograd.Function):
+    """pb_sed weak_label CRNN.review loss (weak_label/crnn.py:117-153); value and gradient
+    come out of the same kernel pass."""
+
+    @staticmethod
+    def forward(ctx, y_fwd, y_bwd, weak, boundary, class_weights, seq, strong_weight, smoothing):
+        y_fwd = _f32c(y_fwd)
+        B, K, T = y_fwd.shape
+        y_bwd = None if y_bwd is None else _f32c(y_bwd)
+        weak = _f32c(weak)
+        boundary = None if boundary is None else _f32c(boundary)
+        cw = None if class_weights is None else _f32c(class_weights)
+        out = torch.empty(2, device=y_fwd.device)
+        ws = torch.empty(2 * B * K + 8, device=y_fwd.device)
+        dyf = torch.empty_like(y_fwd)
+        dyb = None if y_bwd is None else torch.empty_like(y_bwd)
+        call('pbsed_fbcrnn_loss', _ptr(y_fwd), _ptr(y_bwd), _ptr(weak), _ptr(boundary), _ptr(cw),
+             seq.ptr, B, K, T, float(strong_weight), float(smoothing), _ptr(out), _ptr(dyf),
+             _ptr(dyb), _ptr(ws), _stream())
+        ctx.save_for_backward(dyf, dyb)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dl):
+        dyf, dyb = ctx.saved_tensors
+        return (dyf * dl, None if dyb is None else dyb * dl, None, None, None, None, None, None)
+
+
+class BicrnnLossFn(torch.autograd.Function):
+    """pb_sed strong_label CRNN.review loss (strong_label/crnn.py:107-112)."""
+
+    @staticmethod
+    def forward(ctx, y, strong, seq):
+        y = _f32c(y)
+        B, K, T = y.shape
+        strong = _f32c(strong)
+        out = torch.empty(2, device=y.device)
+        ws = torch.empty(8, device=y.device)
+        dy = torch.empty_like(y)
+        call('pbsed_bicrnn_loss', _ptr(y), _ptr(strong), seq.ptr, B, K, T, _ptr(out), _ptr(dy),
+             _ptr(ws), _stream())
+        ctx.save_for_backward(dy)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, dl):
+        dy, = ctx.saved_tensors
+        return dy * dl, None, None
+
+
+# ------------------------------------------------------------------ features
+def logmel_from_audio(audio, stft_cfg, fb, seq, stats):
+    """audio (B,S) -> log-mel (B, n_mels, T) (+ accumulates per-band stats)."""
+    audio = _f32c(audio)
+    B, S = audio.shape
+    T = stft_cfg['T']
+    out = torch.empty((B, fb['n_mels'], T), device=audio.device)
+    call('pbsed_stft_logmel', _ptr(audio), B, S, stft_cfg['shift'], stft_cfg['window_length'],
+         stft_cfg['size'], stft_cfg['pad_front'], T, _ptr(stft_cfg['window']), _ptr(fb['lo']),
+         _ptr(fb['hi']), _ptr(fb['w']), fb['stride'], fb['n_mels'], seq.ptr, _ptr(out),
+         _ptr(stats), _stream())
+    return out
+
+
+def logmel_from_stft(stft, fb, seq, stats):
+    """stft (B,T,F,2) -> log-mel (B, n_mels, T)."""
+    stft = _f32c(stft)
+    B, T, n_bins, two = stft.shape
+    assert two == 2
+    out = torch.empty((B, fb['n_mels'], T), device=stft.device)
+    call('pbsed_spec_logmel', _ptr(stft), B, T, n_bins, _ptr(fb['lo']), _ptr(fb['hi']), _ptr(fb['w']),
+         fb['stride'], fb['n_mels'], seq.ptr, _ptr(out), _ptr(stats), _stream())
+    return out
+
+
+def norm_finalize(stats, count, nch, gamma, beta, eps, momentum, training, rmean, rpower, ntracked,
+                  device):
+    scale = torch.empty(nch, device=device)
+    shift = torch.empty(nch, device=device)
+    call('pbsed_norm_finalize', _ptr(stats), float(count), nch, _ptr(gamma), _ptr(beta), float(eps),
+         float(momentum), int(training), _ptr(rmean), _ptr(rpower), _ptr(ntracked), _ptr(scale),
+         _ptr(shift), None, None, _stream())
+    return scale, shift
+
+
+def logmel_normalize_(x, scale, shift, clamp, seq):
+    B, F, T = x.shape
+    call('pbsed_logmel_normalize', _ptr(x), B, F, T, _ptr(scale), _ptr(shift), float(clamp or 0.),
+         seq.ptr, _stream())
+    return x

@@ -1,0 +1,178 @@
+"""Train-step plumbing: flat parameter arena, fused clip+Adam, data-parallel gradient allreduce,
+CUDA-graph capture of the whole step.
+
+Mirrors the slice of ``padertorch.train`` pb_sed drives
+(pb_sed/experiments/weak_label_crnn/training.py:264-269 optimizer, :377-396 LR schedule,
+:397-400 ``trainer.train``; step body per SURVEY App. A):
+    forward -> review -> loss.backward() -> clip_grad_norm_ -> Adam.step -> zero_grad
+
+* ``FlatArena`` re-homes every trainable parameter (and its ``.grad``) as a view into one
+  contiguous fp32 buffer, so the weight-gradient kernels accumulate straight into the arena,
+  one NCCL all-reduce covers all gradients, and one kernel does norm + clip + Adam.
+* ``Adam`` keeps the padertorch optimizer surface (``lr``, ``gradient_clipping``,
+  ``clip_grad``/``step``/``zero_grad``) on top of ``pbsed_grad_sumsq`` / ``pbsed_adam_step``.
+* ``GraphedTrainStep`` captures forward+loss+backward+optimizer into one CUDA graph over static
+  input buffers (shapes are static for fixed-length clips) and replays it per batch.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import call
+from .ops import _ptr, _stream
+
+
+class FlatArena:
+    def __init__(self, module):
+        params = [p for p in module.parameters() if p.requires_grad]
+        assert params and all(p.is_cuda and p.dtype == torch.float32 for p in params), \
+            'move the model to the GPU (fp32) before building the arena'
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        pad = [(-(s) % 4) for s in sizes]                  # keep every view 16-byte aligned
+        self.n = int(sum(s + q for s, q in zip(sizes, pad)))
+        self.params = torch.zeros(self.n, device=dev)
+        self.grads = torch.zeros(self.n, device=dev)
+        self.exp_avg = torch.zeros(self.n, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n, device=dev)
+        off = 0
+        for p, s, q in zip(params, sizes, pad):
+            view = self.params[off:off + s].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grads[off:off + s].view(p.shape)
+            off += s + q
+        self.module_params = params
+
+    def rebind_grads(self):
+        """re-attach the arena views after something set ``.grad = None``."""
+        off = 0
+        for p in self.module_params:
+            s = p.numel()
+            p.grad = self.grads[off:off + s].view(p.shape)
+            off += s + (-s % 4)
+
+
+class Adam:
+    """padertorch.train.optimizer.Adam surface over the fused kernel (betas/eps = torch defaults)."""
+
+    def __init__(self, model, lr=5e-4, gradient_clipping=1e10, betas=(0.9, 0.999), eps=1e-8,
+                 process_group=None, distributed=None):
+        self.arena = FlatArena(model)
+        dev = self.arena.params.device
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, gradient_clipping, 0., 1., 0.],
+                                  device=dev, dtype=torch.float32)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.grad_norm = torch.zeros(1, device=dev)
+        self.lr, self.gradient_clipping = lr, gradient_clipping
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.process_group = process_group
+        if self.distributed:
+            self.set_grad_scale(1. / dist.get_world_size(process_group))
+
+    def set_lr(self, lr):
+        """LRAnnealingHook equivalent: the LR is a device scalar, valid under graph replay."""
+        self.lr = lr
+        self.hyper[0:1].copy_(torch.tensor([lr], dtype=torch.float32), non_blocking=True)
+
+    def set_grad_scale(self, s):
+        self.hyper[6:7].copy_(torch.tensor([s], dtype=torch.float32))
+
+    def zero_grad(self):
+        self.arena.grads.zero_()
+
+    def allreduce_grads(self):
+        if self.distributed:
+            dist.all_reduce(self.arena.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def step(self):
+        """all-reduce (if DP) -> global norm -> clip -> Adam -> zero the gradient arena."""
+        self.allreduce_grads()
+        return self.update()
+
+    def update(self):
+        a = self.arena
+        call('pbsed_grad_sumsq', _ptr(a.grads), a.n, _ptr(self.hyper), _ptr(self.sumsq), _stream())
+        call('pbsed_adam_step', _ptr(a.params), _ptr(a.grads), _ptr(a.exp_avg), _ptr(a.exp_avg_sq),
+             a.n, _ptr(self.hyper), _ptr(self.sumsq), _ptr(self.grad_norm), 1, _stream())
+        return self.grad_norm
+
+    clip_grad = step     # norm + clip happen inside the fused step
+
+
+def lr_schedule(iteration, breakpoints):
+    """piecewise-linear LR factor of LRAnnealingHook (training.py:377-396)."""
+    xs = [b[0] for b in breakpoints]
+    ys = [b[1] for b in breakpoints]
+    if iteration >= xs[-1]:
+        return ys[-1]
+    return float(np.interp(iteration, xs, ys))
+
+
+def train_step(model, optimizer, batch):
+    """one eager trainer iteration; returns (loss, grad_norm) device tensors."""
+    model.train()
+    outputs = model(dict(batch))
+    loss = model.review(batch, outputs)['loss']
+    loss.backward()
+    return loss.detach(), optimizer.step()
+
+
+class GraphedTrainStep:
+    """whole train step as ONE CUDA graph.  ``example`` is a batch dict of CUDA tensors whose shapes
+    stay fixed; ``__call__(batch)`` copies the new batch into the static buffers and replays."""
+
+    def __init__(self, model, optimizer, example, warmup=2):
+        self.model, self.optimizer = model, optimizer
+        model.train()
+        saved = getattr(model, 'emit_buffers', None)
+        if saved is not None:
+            model.emit_buffers = False        # no D2H syncs inside the captured region
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # DP: the NCCL all-reduce runs eagerly between two captured graphs
+        self.split = self.optimizer.distributed
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+            if not self.split:
+                self.grad_norm = self.optimizer.update()
+        if self.split:
+            self.graph_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_update):
+                self.grad_norm = self.optimizer.update()
+        self.optimizer.arena.rebind_grads()
+
+    def _fwd_bwd(self):
+        outputs = self.model(dict(self.static))
+        loss = self.model.review(self.static, outputs)['loss']
+        loss.backward()
+        self.outputs = outputs
+        return loss.detach()
+
+    def _body(self):
+        loss = self._fwd_bwd()
+        return loss, self.optimizer.step()
+
+    def load(self, batch):
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self.static[k].copy_(v, non_blocking=True)
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        if self.split:
+            self.optimizer.allreduce_grads()
+            self.graph_update.replay()
+        return self.loss, self.grad_norm

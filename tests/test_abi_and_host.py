@@ -1,0 +1,135 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/pbsed_b200.h declares;
+host-side logic (state-dict layouts, filterbank tables, configs, LR schedule)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM, pt_port as P
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from pb_sed_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 20
+    for name in protos:
+        assert hasattr(built_lib, name), name
+    assert built_lib.pbsed_abi_version() == 1
+    assert built_lib.pbsed_launch_count() >= 0
+
+
+def test_bad_arguments_return_einval_without_touching_the_gpu(built_lib):
+    from pb_sed_b200 import _lib
+    assert built_lib.pbsed_tapgemm(None, None, None, None, None, None, None, None, None, None, None, None) == -1
+    d = _lib.TapGemmDesc()
+    d.B = d.F_in = d.F_out = d.T = d.Cin = d.Cout = 1
+    d.ntaps = 99
+    assert built_lib.pbsed_tapgemm_wgrad(ctypes.byref(d), None, None, None, None, None, 0, None, None, None) == -1
+    assert built_lib.pbsed_gru_fwd(None, 0, None, None, None, 1, 1, 48, 1, None, None, 0, 48, None, None) == -1
+    assert built_lib.pbsed_stft_logmel(None, 1, 1, 1, 1, 8, 0, 1, None, None, None, None, 1, 1, None, None, None, None) == -1
+    with pytest.raises(_lib.PbsedError):
+        _lib.call('pbsed_adam_step', None, None, None, None, 0, None, None, None, 0, None)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from pb_sed_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(RuntimeError, match='no CPU / eager fallback'):
+        _lib.load()
+
+
+def test_ops_refuse_cpu_tensors(built_lib):
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label
+    m = weak_label.CRNN.from_config_dict(config.tiny_fbcrnn_config())
+    b = OM.synthetic_batch(2, num_samples=16 * 20, stft_kwargs=dict(shift=16, window_length=48, size=64))
+    with pytest.raises(AssertionError, match='CUDA tensors only'):
+        m(dict(b))
+
+
+def test_state_dict_interchanges_with_reference_layout():
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label, strong_label
+    for prod, ora in ((weak_label.CRNN.from_config_dict(config.fbcrnn_config()), OM.build_fbcrnn(seed=3)),
+                      (strong_label.CRNN.from_config_dict(config.bicrnn_config()), OM.build_bicrnn(seed=4))):
+        assert sum(p.numel() for p in prod.parameters()) == sum(p.numel() for p in ora.parameters())
+        prod.load_state_dict(ora.state_dict(), strict=True)
+        sd = prod.state_dict()
+        for k, v in ora.state_dict().items():
+            assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+        ora2 = type(ora).__name__
+        fresh = OM.build_fbcrnn(seed=9) if ora2 == 'FBCRNN' else OM.build_bicrnn(seed=9)
+        fresh.load_state_dict(sd, strict=True)          # and back into torch modules
+    assert sum(p.numel() for p in weak_label.CRNN.from_config_dict(config.fbcrnn_config()).parameters()) == 3493188
+
+
+def test_native_conv_weight_layout_is_the_tap_contraction():
+    """native (taps, Cout, Cin) weights + tap offsets == torch conv2d / conv1d / flatten-conv1d."""
+    from pb_sed_b200.modules import _Conv
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 6, 7)                                     # b c f t
+    c2 = _Conv(2, 3, 5, 3)
+    w_ref = c2._to_ref(c2.weight.detach())
+    y_ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), w_ref)
+    xn = x.permute(0, 2, 3, 1)
+    y = torch.zeros(2, 6, 7, 5)
+    for tap, (df, dt) in enumerate(c2.taps):
+        xs = torch.zeros_like(xn)
+        f0, f1 = max(0, -df), min(6, 6 - df)
+        t0, t1 = max(0, -dt), min(7, 7 - dt)
+        xs[:, f0:f1, t0:t1] = xn[:, f0 + df:f1 + df, t0 + dt:t1 + dt]
+        y += xs @ c2.weight[tap].t()
+    assert torch.allclose(y.permute(0, 3, 1, 2), y_ref, atol=1e-5)
+    assert torch.equal(c2._from_ref(w_ref), c2.weight.detach())
+    # flatten conv1d: reference sees (c f) features
+    c1 = _Conv(1, 3, 4, 3, flatten_height=6)
+    w_ref = c1._to_ref(c1.weight.detach())
+    assert w_ref.shape == (4, 18, 3)
+    y_ref = torch.nn.functional.conv1d(torch.nn.functional.pad(x.reshape(2, 18, 7), (1, 1)), w_ref)
+    y = torch.zeros(2, 7, 4)
+    for tap, (f, dt) in enumerate(c1.taps):
+        xs = torch.zeros(2, 7, 3)
+        t0, t1 = max(0, -dt), min(7, 7 - dt)
+        xs[:, t0:t1] = xn[:, f, t0 + dt:t1 + dt]
+        y += xs @ c1.weight[tap].t()
+    assert torch.allclose(y.transpose(1, 2), y_ref, atol=1e-5)
+    assert torch.equal(c1._from_ref(w_ref), c1.weight.detach())
+
+
+def test_feature_tables_match_oracle():
+    from pb_sed_b200 import modules as M
+    fb = M.mel_filterbank(16000, 1024, 128)
+    assert np.allclose(fb, P.get_fbanks(16000, 1024, 128), atol=1e-12)
+    lo, hi, w, stride = M.sparse_filterbank(fb.astype(np.float32))
+    dense = np.zeros_like(fb, dtype=np.float32)
+    for m in range(128):
+        dense[m, lo[m]:hi[m]] = w[m, :hi[m] - lo[m]]
+    assert np.array_equal(dense, fb.astype(np.float32))
+    assert np.allclose(M.blackman_window(960), P.blackman_periodic(960))
+    for n in (160000, 645, 47, 1):
+        assert M.stft_num_frames(n, 320, 960) == P.stft_frames(n, 320, 960)
+    assert M.stft_num_frames(160000, 320, 960) == 500
+
+
+def test_lr_schedule_matches_training_script():
+    """breakpoints of pb_sed/experiments/weak_label_crnn/training.py:377-387 at batch size 32."""
+    from pb_sed_b200.train import lr_schedule
+    bp = [(0, 0.), (1000, 1.), (10000, 1.), (10000, .2)]
+    assert lr_schedule(0, bp) == 0. and lr_schedule(500, bp) == 0.5
+    assert lr_schedule(5000, bp) == 1. and lr_schedule(10001, bp) == .2
+
+
+def test_reduce_and_mask_helpers_match_oracle():
+    from pb_sed_b200 import modules as M
+    x = torch.randn(3, 4, 9)
+    sl = np.array([9, 5, 1])
+    for name in ('Sum', 'Mean', 'TakeLast'):
+        a = getattr(M, name)(axis=-1)(x, sl)
+        b = getattr(P, name)(axis=-1)(x, sl)
+        assert torch.equal(a, b), name
+    assert torch.equal(M.Max(axis=-1)(x, sl)[0], P.Max(axis=-1)(x, sl)[0])
+    assert torch.equal(M.compute_mask(x, sl, 0, -1), P.compute_mask(x, sl, 0, -1))
+    assert torch.equal(M.Pad('both')(x, 5), P.Pad('both')(x, 5))

@@ -1,0 +1,339 @@
+"""GPU (-m gpu): the sm_100a kernels, called through the C ABI, against the CPU oracle and the
+committed golden vectors.  Tolerances are written next to each comparison; 'logits' are the
+pre-sigmoid output_net outputs (BASELINE.json: frame-logit max|delta| <= 1e-3)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import models as OM, pt_port as P
+from util import load_golden, golden_batch, ref_layout_grads, maxdiff, reldiff, TINY_STFT
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _lib_loaded(built_lib):
+    assert torch.cuda.is_available()
+    yield
+
+
+def tiny_pair(seed=0, **kw):
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label
+    ora = OM.tiny_fbcrnn(seed=seed, **kw)
+    prod = weak_label.CRNN.from_config_dict(config.tiny_fbcrnn_config(**kw))
+    prod.load_state_dict(ora.state_dict())
+    return ora, prod.to(DEV)
+
+
+# ------------------------------------------------------------------ K1 features
+@pytest.mark.parametrize('S,kw,n_mels', [(645, TINY_STFT, 16), (16000, dict(shift=320, window_length=960, size=1024), 128),
+                                          (3000, dict(shift=160, window_length=400, size=512), 80)])
+def test_stft_logmel_matches_float64_oracle(S, kw, n_mels):
+    from pb_sed_b200.modules import NormalizedLogMelExtractor
+    audio = OM.synthetic_audio(3, S, seed=7)
+    spec = P.stft(audio, **kw)
+    stft = torch.from_numpy(np.stack([spec.real, spec.imag], -1).astype(np.float32))
+    T = stft.shape[2]
+    seq_len = [T, T - 1, max(T // 2, 1)]
+    ora = P.NormalizedLogMelExtractor(16000, kw['size'], n_mels).train()
+    fe = NormalizedLogMelExtractor(16000, kw['size'], n_mels, stft_kwargs=kw).to(DEV).train()
+    y_ref, _ = ora(stft, seq_len=np.array(seq_len))
+    y_audio, _ = fe(torch.from_numpy(audio).to(DEV), seq_len=np.array(seq_len))
+    assert y_audio.shape == y_ref.shape
+    # normalised, clamped log-mel from raw audio (fp32 FFT on the GPU vs float64 numpy rfft): 2e-3
+    assert maxdiff(y_audio, y_ref) < 2e-3
+    fe2 = NormalizedLogMelExtractor(16000, kw['size'], n_mels, stft_kwargs=kw).to(DEV).train()
+    y_stft, _ = fe2(stft.to(DEV), seq_len=np.array(seq_len))
+    assert maxdiff(y_stft, y_ref) < 1e-4            # same float32 STFT in: 1e-4
+    for k, v in ora.state_dict().items():           # running statistics updated identically
+        assert maxdiff(fe2.state_dict()[k], v) < 1e-4 * max(1., float(v.abs().max())), k
+    # second batch (cumulative statistics) + eval mode
+    y_ref2, _ = ora(stft.flip(0), seq_len=np.array(seq_len))
+    y2, _ = fe2(stft.flip(0).to(DEV), seq_len=np.array(seq_len))
+    assert maxdiff(y2, y_ref2) < 1e-4
+    ora.eval(); fe2.eval()
+    assert maxdiff(fe2(stft.to(DEV), seq_len=np.array(seq_len))[0], ora(stft, seq_len=np.array(seq_len))[0]) < 1e-4
+
+
+# ------------------------------------------------------------------ K2 tap-GEMM
+@pytest.mark.parametrize('B,Cin,Cout,Fh,T,k', [(2, 1, 16, 12, 37, 3), (2, 16, 16, 8, 130, 3), (1, 11, 24, 6, 50, 3),
+                                                (2, 32, 64, 4, 129, 3), (1, 64, 256, 2, 70, 3)])
+def test_conv2d_forward_backward_vs_torch(B, Cin, Cout, Fh, T, k):
+    from pb_sed_b200 import ops
+    from pb_sed_b200.modules import _Conv
+    torch.manual_seed(Cin * 7 + Cout)
+    conv = _Conv(2, Cin, Cout, k).to(DEV)
+    with torch.no_grad():
+        conv.bias.uniform_(-.5, .5)
+    x = torch.randn(B, Cin, Fh, T)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    seq = ops.SeqLen.make(None, B, T, DEV)
+    cfg = dict(F_in=Fh, F_out=Fh, taps=conv.taps, relu=False, per_f=False, pool=1, norm=False,
+               eps=0., momentum=0., training=True)
+    y = ops.ConvLayerFn.apply(xg, conv.weight, conv.bias, None, None, None, None, None, seq, cfg)
+    xr = x.clone().requires_grad_(True)
+    w = conv._to_ref(conv.weight.detach().cpu()).requires_grad_(True)
+    b = conv.bias.detach().cpu().clone().requires_grad_(True)
+    yr = F.conv2d(F.pad(xr, (1, 1, 1, 1)), w, b)
+    assert reldiff(y.permute(0, 3, 1, 2), yr) < 1e-5          # exact-fp32 FFMA path
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    y.backward(g.permute(0, 2, 3, 1).contiguous().to(DEV))
+    assert reldiff(xg.grad.permute(0, 3, 1, 2), xr.grad) < 1e-5
+    assert reldiff(conv._to_ref(conv.weight.grad.cpu()), w.grad) < 1e-4
+    assert reldiff(conv.bias.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize('seq_len', [None, [21, 20, 13, 5]])
+def test_cnn_stack_train_mode_vs_oracle(seq_len):
+    """norm(batch stats, masked) -> relu -> conv -> pool chain, flatten, 1-D stack; fwd + all grads."""
+    from pb_sed_b200 import modules as M
+    torch.manual_seed(1)
+    kw2 = dict(in_channels=1, out_channels=[8, 8, 16], kernel_size=3, pool_size=[1, (2, 1), (2, 1)], norm='batch',
+               norm_kwargs={'eps': 1e-3}, pre_activation=True, output_layer=False)
+    kw1 = dict(out_channels=[32, 32], kernel_size=[3, 1], norm='batch', norm_kwargs={'eps': 1e-3},
+               pre_activation=True, output_layer=False)
+    ora = P.CNN(P.CNN2d(**kw2), P.CNN1d(in_channels=64, input_layer=False, **kw1), input_height=16).train()
+    prod = M.CNN(kw2, kw1, input_height=16)
+    prod.load_state_dict(ora.state_dict())
+    prod.to(DEV).train()
+    x = torch.randn(4, 1, 16, 21)
+    sl = None if seq_len is None else np.array(seq_len)
+    if sl is not None:
+        x = x * P.compute_mask(x, sl, 0, -1)
+    h_ref, _ = ora(x, sl)
+    h, _ = prod(x.to(DEV), sl)
+    mask = P.compute_mask(h_ref, sl, 0, -1)
+    assert maxdiff(h.cpu() * mask, h_ref * mask) < 1e-4
+    g = torch.randn_like(h_ref) * mask
+    h_ref.backward(g)
+    h.backward(g.to(DEV))
+    grads = ref_layout_grads(prod)
+    for k, p in ora.named_parameters():
+        assert maxdiff(grads[k], p.grad) < 2e-4 * max(1., float(p.grad.abs().max())), k
+    for k, v in ora.state_dict().items():          # running statistics
+        assert maxdiff(prod.state_dict()[k], v) < 1e-4 * max(1., float(v.abs().max())), k
+    ora.eval(); prod.eval()
+    with torch.no_grad():
+        assert maxdiff(prod(x.to(DEV), sl)[0].cpu() * mask, ora(x, sl)[0] * mask) < 1e-4
+
+
+# ------------------------------------------------------------------ K3 GRU
+@pytest.mark.parametrize('H,In,layers,bidir,reverse,seq_len', [
+    (32, 32, 2, False, False, None), (32, 20, 1, False, True, [15, 14, 9, 9, 3, 1, 1, 15, 2]),
+    (64, 42, 2, True, False, [15, 14, 9, 9, 3, 1, 1, 15, 2]), (256, 256, 2, False, True, [15, 15, 7, 2, 1, 15, 15, 15, 11]),
+    (128, 64, 1, True, False, None)])
+def test_gru_forward_backward_vs_torch(H, In, layers, bidir, reverse, seq_len):
+    from pb_sed_b200 import modules as M
+    torch.manual_seed(H + In)
+    B, T, K = 9, 15, 10
+    out_kw = dict(out_channels=[16, K], kernel_size=1, norm='batch', norm_kwargs={'eps': 1e-3})
+    gru = torch.nn.GRU(In, H, num_layers=layers, batch_first=True, bidirectional=bidir)
+    ora = P.GRU(gru, P.CNN1d(H * (2 if bidir else 1), **out_kw, pre_activation=False, output_layer=True),
+                reverse=reverse).train()
+    prod = M.GRU(dict(input_size=In, hidden_size=H, num_layers=layers, bidirectional=bidir), out_kw, reverse=reverse)
+    prod.load_state_dict(ora.state_dict())
+    prod.to(DEV).train()
+    sl = None if seq_len is None else np.array(seq_len)
+    x = torch.randn(B, In, T)
+    xr = x.clone().requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    y_ref, _ = ora(xr, sl)
+    y, _ = prod(xg, sl)
+    mask = P.compute_mask(y_ref, sl, 0, -1)
+    assert maxdiff(y.cpu() * mask, y_ref * mask) < 1e-4
+    g = torch.randn_like(y_ref) * mask
+    y_ref.backward(g)
+    y.backward(g.to(DEV))
+    xmask = P.compute_mask(x, sl, 0, -1)
+    assert maxdiff(xg.grad.cpu() * xmask, xr.grad * xmask) < 1e-4
+    grads = ref_layout_grads(prod)
+    for k, p in ora.named_parameters():
+        assert maxdiff(grads[k], p.grad) < 2e-4 * max(1., float(p.grad.abs().max())), k
+
+
+# ------------------------------------------------------------------ K4 losses
+@pytest.mark.parametrize('strong_weight,with_bwd,smoothing,seq_len', [
+    (1., True, 0., None), (1., True, 0.05, [50, 47, 30, 1, 12]), (0., True, 0., [50, 47, 30, 1, 12]),
+    (1., False, 0., [50, 47, 30, 2, 12]), (.5, True, 0., [50, 50, 50, 50, 50])])
+def test_fbcrnn_loss_value_and_gradient(strong_weight, with_bwd, smoothing, seq_len):
+    from pb_sed_b200 import ops
+    torch.manual_seed(3)
+    B, K, T = 5, 7, 50
+    yf = torch.rand(B, K, T).clamp(1e-5, 1 - 1e-5).requires_grad_(True)
+    yb = torch.rand(B, K, T).clamp(1e-5, 1 - 1e-5).requires_grad_(True) if with_bwd else None
+    weak, boundary = OM.synthetic_targets(B, K, T, seed=3, seq_len=seq_len)
+    weak, boundary = torch.from_numpy(weak), torch.from_numpy(boundary)
+    weak[0, 0] = .5                      # unknown weak label
+    boundary[1, :, 10:14] = .5           # partially unknown boundaries
+    cw = torch.rand(K) + .5
+    m = OM.FBCRNN(None, None, None, None, strong_fwd_bwd_loss_weight=strong_weight,
+                  label_smoothing=smoothing, class_weights=cw.tolist())
+    sl = None if seq_len is None else np.array(seq_len)
+    ref = m.loss(yf, yb, sl, (weak, boundary))
+    ref.backward()
+    yfg = yf.detach().to(DEV).requires_grad_(True)
+    ybg = yb.detach().to(DEV).requires_grad_(True) if with_bwd else None
+    seq = ops.SeqLen.make(sl, B, T, DEV)
+    loss = ops.FbcrnnLossFn.apply(yfg, ybg, weak.to(DEV), boundary.to(DEV), cw.to(DEV), seq, strong_weight, smoothing)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1., abs(float(ref)))
+    assert maxdiff(yfg.grad, yf.grad) < 1e-5 * max(1., float(yf.grad.abs().max()))
+    if with_bwd:
+        assert maxdiff(ybg.grad, yb.grad) < 1e-5 * max(1., float(yb.grad.abs().max()))
+
+
+def test_bicrnn_loss_value_and_gradient():
+    from pb_sed_b200 import ops
+    torch.manual_seed(4)
+    B, K, T = 4, 6, 33
+    y = torch.rand(B, K, T).clamp(1e-6, 1 - 1e-6).requires_grad_(True)
+    st = (torch.rand(B, K, T) > .7).float()
+    st[0, :, 3:9] = .5
+    sl = np.array([33, 20, 7, 1])
+    ref = OM.BiCRNN(None, None, None).loss(y, sl, (None, st))
+    ref.backward()
+    yg = y.detach().to(DEV).requires_grad_(True)
+    loss = ops.BicrnnLossFn.apply(yg, st.to(DEV), ops.SeqLen.make(sl, B, T, DEV))
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5
+    assert maxdiff(yg.grad, y.grad) < 1e-6 * max(1., float(y.grad.abs().max()))
+
+
+# ------------------------------------------------------------------ K5 optimizer
+def test_fused_clip_adam_vs_torch():
+    from pb_sed_b200 import train
+    torch.manual_seed(5)
+    for clip in (1e10, 0.1):
+        ref = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 3))
+        prod = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Linear(19, 3))
+        prod.load_state_dict(ref.state_dict())
+        prod.to(DEV)
+        opt_ref = torch.optim.Adam(ref.parameters(), lr=5e-4)
+        opt = train.Adam(prod, lr=5e-4, gradient_clipping=clip)
+        for it in range(4):
+            x = torch.randn(8, 37)
+            ref(x).pow(2).sum().backward()
+            prod(x.to(DEV)).pow(2).sum().backward()
+            gn_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+            opt_ref.step(); opt_ref.zero_grad()
+            gn = opt.step()
+            assert abs(float(gn) - float(gn_ref)) < 1e-4 * float(gn_ref)
+            assert float(opt.arena.grads.abs().max()) == 0.
+            for p, q in zip(prod.parameters(), ref.parameters()):
+                assert maxdiff(p, q) < 2e-6, it
+
+
+# ------------------------------------------------------------------ whole model
+@pytest.mark.parametrize('name', ['fbcrnn_tiny_full', 'fbcrnn_tiny_ragged', 'fbcrnn_tiny_weakonly'])
+@pytest.mark.parametrize('from_audio', [False, True])
+def test_fbcrnn_matches_golden(name, from_audio):
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label
+    d, state, grads = load_golden(name)
+    model = weak_label.CRNN.from_config_dict(config.tiny_fbcrnn_config(strong_fwd_bwd_loss_weight=float(d['strong_weight'])))
+    model.load_state_dict(state)
+    model.to(DEV).train()
+    batch = golden_batch(d, ['weak_targets', 'boundary_targets'], DEV, stft=not from_audio)
+    out = model(dict(batch))
+    review = model.review(batch, out)
+    review['loss'].backward()
+    tol = 2e-3 if from_audio else 2e-4     # scores in (0,1); audio path adds the fp32-FFT difference
+    sl = d['seq_len']
+    mask = P.compute_mask(torch.from_numpy(d['y_fwd']), sl, 0, -1)
+    assert maxdiff(out[0].cpu() * mask, torch.from_numpy(d['y_fwd']) * mask) < tol
+    assert maxdiff(out[1].cpu() * mask, torch.from_numpy(d['y_bwd']) * mask) < tol
+    assert maxdiff(out[3], d['features']) < (2e-3 if from_audio else 1e-4)
+    assert abs(float(review['loss']) - float(d['loss'])) < tol
+    assert maxdiff(review['buffers']['y_weak'], d['y_weak']) < tol
+    if not from_audio:
+        g = ref_layout_grads(model)
+        for k, v in grads.items():
+            assert maxdiff(g[k], v) < 5e-4 * max(1., float(v.abs().max())), k
+    model.eval()
+    with torch.no_grad():
+        assert maxdiff(model.tagging(batch)[0], d['tagging']) < tol
+        assert maxdiff(model.boundaries_detection(batch)[0], d['boundaries']) < tol
+        sed, sed_len = model.sound_event_detection(batch, window_length=5, window_shift=2)
+        assert maxdiff(sed, d['sed']) < tol and np.array_equal(sed_len, d['sed_len'])
+
+
+def test_bicrnn_matches_golden():
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import strong_label
+    d, state, grads = load_golden('bicrnn_tiny_ragged')
+    cfg = config.bicrnn_config(**{k: v for k, v in dict(
+        stft_size=64, number_of_filters=16, out_channels_2d=[8, 8, 16], pool_sizes_2d=[1, (2, 1), (2, 1)],
+        out_channels_1d=[32, 32], kernel_size_1d=[3, 1], hidden_size=32, out_hidden=16,
+        stft_kwargs=dict(shift=16, window_length=48)).items()})
+    model = strong_label.CRNN.from_config_dict(cfg)
+    model.load_state_dict(state)
+    model.to(DEV).train()
+    batch = golden_batch(d, ['weak_targets', 'strong_targets', 'tag_condition'], DEV)
+    out = model(dict(batch))
+    review = model.review(batch, out)
+    review['loss'].backward()
+    mask = P.compute_mask(torch.from_numpy(d['y']), d['seq_len'], 0, -1)
+    assert maxdiff(out[0].cpu() * mask, torch.from_numpy(d['y']) * mask) < 2e-4
+    assert abs(float(review['loss']) - float(d['loss'])) < 2e-4
+    g = ref_layout_grads(model)
+    for k, v in grads.items():
+        assert maxdiff(g[k], v) < 5e-4 * max(1., float(v.abs().max())), k
+    model.eval()
+    with torch.no_grad():
+        assert maxdiff(model.sound_event_detection(batch)[0], d['sed']) < 2e-4
+
+
+def test_full_size_fbcrnn_logits_and_train_step_vs_oracle():
+    """the reference's default FBCRNN (3.49 M params) on 2 x 10 s clips: frame logits within 1e-3
+    max-abs of the CPU oracle (BASELINE.json north_star), loss / grad-norm / Adam update agree."""
+    from pb_sed_b200 import config, train
+    from pb_sed_b200.models import weak_label
+    ora = OM.build_fbcrnn(seed=0)
+    model = weak_label.CRNN.from_config_dict(config.fbcrnn_config())
+    model.load_state_dict(ora.state_dict())
+    model.to(DEV)
+    model.emit_buffers = False
+    batch = OM.synthetic_batch(2, seed=11)
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'stft'}
+    opt = train.Adam(model, lr=5e-4)
+    model.train()
+    out = model(dict(gb))
+    loss = model.review(gb, out)['loss']
+    loss.backward()
+    z_fwd, z_bwd = model._z_fwd.detach().cpu(), model._z_bwd.detach().cpu()
+    gnorm = opt.step()
+    ora.train()
+    cb = {k: v for k, v in batch.items() if k != 'audio_data'}
+    zr_fwd, zr_bwd, *_ = ora.logits(cb)
+    # logits() advanced the oracle's running statistics once; rebuild for the train step
+    ora2 = OM.build_fbcrnn(seed=0)
+    ref_loss, ref_gnorm, _ = OM.train_step(ora2, OM.make_adam(ora2), cb)
+    assert maxdiff(z_fwd.transpose(1, 2), zr_fwd) < 1e-3      # frame logits, fwd GRU head
+    assert maxdiff(z_bwd.transpose(1, 2), zr_bwd) < 1e-3      # frame logits, bwd GRU head
+    assert abs(float(loss) - float(ref_loss)) < 1e-4
+    assert abs(float(gnorm) - float(ref_gnorm)) < 1e-3 * float(ref_gnorm)
+
+
+def test_graphed_train_step_equals_eager():
+    from pb_sed_b200 import train
+    ora, m1 = tiny_pair(seed=2)
+    _, m2 = tiny_pair(seed=2)
+    batch = OM.synthetic_batch(4, num_samples=645, stft_kwargs=TINY_STFT, seed=2)
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'stft'}
+    o1, o2 = train.Adam(m1, lr=1e-3), train.Adam(m2, lr=1e-3)
+    m1.emit_buffers = False
+    step = train.GraphedTrainStep(m2, o2, gb, warmup=2)
+    for _ in range(2):
+        train.train_step(m1, o1, gb)
+    for it in range(3):
+        l1, g1 = train.train_step(m1, o1, gb)
+        l2, g2 = step(gb)
+        assert abs(float(l1) - float(l2)) < 1e-5 and abs(float(g1) - float(g2)) < 1e-4 * float(g1)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert maxdiff(a, b) < 1e-5, k
