@@ -80,10 +80,23 @@ class PbsedError(RuntimeError):
     pass
 
 
+# optional per-call device timing (bench.py's roofline pass): set to a list to record
+# (name, start_event, end_event, args) for every C-ABI call made while it is set.
+profile_sink = None
+
+
 def call(name, *args):
     """call an int-returning entry point; raise on a non-zero status."""
     fn = getattr(load(), name)
-    rc = fn(*args)
+    if profile_sink is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        profile_sink.append((name, e0, e1, args))
+    else:
+        rc = fn(*args)
     if rc != 0:
         kind = {-1: 'PBSED_EINVAL (bad argument / unsupported shape)',
                 -2: 'PBSED_EWORKSPACE'}.get(rc, f'cudaError {rc}' if rc > 0 else str(rc))

@@ -37,7 +37,7 @@ class CRNN(base.SoundEventModel):
         if self.tag_conditioning:
             h = ops.ConcatCondFn.apply(h, tags)
         z = self.rnn.forward_native(h, seq)
-        self._z = z
+        self._z = z.detach()
         return ops.SigmoidScoresFn.apply(z, 0.), seq_len_x, x, seq_len_x, targets
 
     def loss(self, y, seq_len_y, targets):

@@ -71,10 +71,12 @@ class CRNN(base.SoundEventModel):
 
     def forward(self, inputs):
         h, seq, x, seq_len_x, targets = self.encode(inputs, pop=self.training)
-        y_fwd, self._z_fwd = self._scores_native(self.rnn_fwd, h, seq)
+        y_fwd, z = self._scores_native(self.rnn_fwd, h, seq)
+        self._z_fwd = z.detach()              # frame logits (B,T,K), kept for the parity metric
         y_bwd = None
         if self.rnn_bwd is not None:
-            y_bwd, self._z_bwd = self._scores_native(self.rnn_bwd, h, seq)
+            y_bwd, z = self._scores_native(self.rnn_bwd, h, seq)
+            self._z_bwd = z.detach()
         if seq_len_x is None:
             seq_len_x = np.full(x.shape[0], x.shape[-1])
         return y_fwd, y_bwd, seq_len_x, x, seq_len_x, targets

@@ -190,7 +190,10 @@ class ConvLayerFn(torch.autograd.Function):
                      cfg['momentum'], 0, _ptr(rmean), _ptr(rpower), _ptr(ntracked), _ptr(scale),
                      _ptr(shift), None, None, _stream())
         desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f)
-        z = tapgemm(x, weight, bias, desc, scale, shift, seq).view(B, F_out, T, Cout)
+        # the reference masks padded frames inside Normalization only: a bare conv (layer 0, whose
+        # tag-condition channels are NOT zero at padded frames) reads its input unmasked
+        load_seq = seq if cfg['norm'] else None
+        z = tapgemm(x, weight, bias, desc, scale, shift, load_seq).view(B, F_out, T, Cout)
         idx = None
         if pool > 1:
             y = torch.empty((B, F_out // pool, T, Cout), device=x.device)
@@ -221,7 +224,7 @@ class ConvLayerFn(torch.autograd.Function):
         dW, dW_ret = _grad_target(w_p)
         db, db_ret = _grad_target(b_p)
         if dW is not None:
-            tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq, mask_out=False)
+            tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq if cfg['norm'] else None, mask_out=False)
         dx = dg_ret = dbe_ret = None
         if ctx.needs_input_grad[0]:
             rtaps = [(-df, -dt) for df, dt in cfg['taps']]

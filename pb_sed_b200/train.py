@@ -156,7 +156,9 @@ class GraphedTrainStep:
         outputs = self.model(dict(self.static))
         loss = self.model.review(self.static, outputs)['loss']
         loss.backward()
-        self.outputs = outputs
+        # keep only detached results: a live autograd graph would pin its AccumulateGrad nodes to the
+        # warm-up stream and poison the capture with a cross-stream dependency
+        self.outputs = tuple(o.detach() if torch.is_tensor(o) else o for o in outputs)
         return loss.detach()
 
     def _body(self):
