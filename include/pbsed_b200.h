@@ -164,28 +164,31 @@ int pbsed_split_cond_bwd(const float* dout, int B, int F, int T, int C0, int K, 
  * K3  GRU recurrence   (replaces torch.nn.GRU inside padertorch.contrib.je.modules.rnn.GRU,
  *     call sites pb_sed/models/weak_label/crnn.py:62,66 and strong_label/crnn.py:92)
  *
- * One launch runs `ndir` independent directions of ONE layer.  Direction d uses
- *   gi   + d*gi_dir_stride   : (B,T,3H) input projection x@W_ih^T + b_ih  (gate order r,z,n)
- *   w_hh + d*3H*H            : (3H,H),   b_hh + d*3H : (3H)
- *   reverse[d] != 0          : time runs seq_len[b]-1 .. 0 (the reference's reverse=True /
- *                              the backward direction of bidirectional=True)
- *   h_out + d*h_dir_off      : (B,T,h_stride) rows, writes H channels (zeros at t >= seq_len[b])
- *   save + d*B*T*4H          : (B,T,4H) = r, z, n, (W_hn h + b_hn)  for backward (nullable)
+ * One launch runs `ndir` (<= 4) independent recurrences of the same shape -- the two directions of
+ * a bidirectional layer, or the same layer of the reference's separate rnn_fwd / rnn_bwd modules.
+ * Every operand is a HOST array of `ndir` device pointers:
+ *   gi[d]    : (B,T,3H) input projection x@W_ih^T + b_ih  (gate order r,z,n)
+ *   w_hh[d]  : (3H,H),   b_hh[d] : (3H)
+ *   reverse_host[d] != 0 : time runs seq_len[b]-1 .. 0 (the reference's reverse=True / the backward
+ *                          direction of bidirectional=True)
+ *   h_out[d] : rows (B,T,h_stride), H channels written (zeros at t >= seq_len[b]); a bidirectional
+ *              layer passes h_out[1] = h_out[0] + H with h_stride = 2H
+ *   save[d]  : (B,T,4H) = r, z, n, (W_hn h + b_hn)  for backward (save or save[d] nullable)
  * H must be a multiple of 32 and <= 256 (one thread-block cluster of H/32 CTAs per 8-clip batch
  * slice and direction, W_hh resident in registers); h0 = 0.
  */
-int pbsed_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh, const float* b_hh,
+int pbsed_gru_fwd(const float* const* gi, const float* const* w_hh, const float* const* b_hh,
                   const int* seq_len, int B, int T, int H, int ndir, const int* reverse_host,
-                  float* h_out, long long h_dir_off, int h_stride, float* save, void* stream);
-/* backward through time.  dh_out: gradient w.r.t. h_out (same addressing as h_out).
- * writes dgi (B,T,3H per dir, stride gi_dir_stride) = dL/d(gi) = [dr, dz, dn] and
- * dgh (same addressing) = dL/d(W_hh h + b_hh) = [dr, dz, dn*r]; zeros at t >= seq_len[b].
- * The weight gradients are then plain tap-GEMM wgrads (dW_ih: dgi x input, dW_hh: dgh x h_out
- * shifted one step against the direction of time, dt = -1 / +1 with seq_len masking). */
-int pbsed_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride,
-                  const float* h_out, const float* save, const float* w_hh,
-                  const int* seq_len, int B, int T, int H, int ndir, const int* reverse_host,
-                  float* dgi, float* dgh, long long gi_dir_stride, void* stream);
+                  float* const* h_out, int h_stride, float* const* save, void* stream);
+/* backward through time.  dh_out[d]: gradient w.r.t. h_out[d] (same addressing).
+ * writes dgi[d] (B,T,3H) = dL/d(gi) = [dr, dz, dn] and dgh[d] (B,T,3H) = dL/d(W_hh h + b_hh) =
+ * [dr, dz, dn*r]; zeros at t >= seq_len[b].  The weight gradients are then plain tap-GEMM wgrads
+ * (dW_ih: dgi x input, dW_hh: dgh x h_out shifted one step against the direction of time,
+ * dt = -1 / +1 with seq_len masking). */
+int pbsed_gru_bwd(const float* const* dh_out, const float* const* h_out, const float* const* save,
+                  const float* const* w_hh, const int* seq_len, int B, int T, int H, int ndir,
+                  const int* reverse_host, float* const* dgi, float* const* dgh, int h_stride,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------
  * K4  scores + losses

@@ -20,16 +20,23 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-struct GruDirs { int reverse[4]; };
+struct GruDirs {             // per-direction operands: directions may belong to different modules
+  int reverse[4];
+  const float* gi[4];        // (B,T,3H)
+  const float* w_hh[4];      // (3H,H)
+  const float* b_hh[4];      // (3H)
+  float* h_out[4];           // rows (B,T,h_stride), H channels written
+  float* save[4];            // (B,T,4H) or null
+  const float* dh_out[4];    // backward: gradient w.r.t. h_out
+  float* dgi[4];             // backward outputs (B,T,3H)
+  float* dgh[4];
+};
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 template <int H>
 __global__ void __launch_bounds__(256, 1)
-gru_fwd_kernel(const float* __restrict__ gi, long long gi_dir_stride, const float* __restrict__ w_hh,
-               const float* __restrict__ b_hh, const int* __restrict__ seq_len, int B, int T,
-               GruDirs dirs, float* __restrict__ h_out, long long h_dir_off, int h_stride,
-               float* __restrict__ save) {
+gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int h_stride) {
   constexpr int NC = H / 32, KS = H / 8, BC = 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -42,8 +49,8 @@ gru_fwd_kernel(const float* __restrict__ gi, long long gi_dir_stride, const floa
   __shared__ __align__(16) float hbuf[2][BC][H];
   __shared__ float red[8][3][BC][32];
 
-  const float* w = w_hh + (long long)d * 3 * H * H;
-  const float* bh = b_hh + (long long)d * 3 * H;
+  const float* w = dirs.w_hh[d];
+  const float* bh = dirs.b_hh[d];
   float W[3][KS];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
@@ -53,9 +60,9 @@ gru_fwd_kernel(const float* __restrict__ gi, long long gi_dir_stride, const floa
 
   for (int i = tid; i < 2 * BC * H; i += 256) (&hbuf[0][0][0])[i] = 0.f;
   const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
-  const float* gi_b = gi + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
-  float* ho_b = h_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
-  float* sv_b = save ? save + ((long long)d * B + bq) * T * 4 * H : nullptr;
+  const float* gi_b = dirs.gi[d] + (long long)bq * T * 3 * H;
+  float* ho_b = dirs.h_out[d] + (long long)bq * T * h_stride;
+  float* sv_b = dirs.save[d] ? dirs.save[d] + (long long)bq * T * 4 * H : nullptr;
   float hprev = 0.f;
   cluster.sync();
 
@@ -122,11 +129,7 @@ gru_fwd_kernel(const float* __restrict__ gi, long long gi_dir_stride, const floa
 // ------------------------------------------------------------------ BPTT
 template <int H>
 __global__ void __launch_bounds__(256, 1)
-gru_bwd_kernel(const float* __restrict__ dh_out, long long h_dir_off, int h_stride,
-               const float* __restrict__ h_out, const float* __restrict__ save,
-               const float* __restrict__ w_hh, const int* __restrict__ seq_len, int B, int T,
-               GruDirs dirs, float* __restrict__ dgi, float* __restrict__ dgh,
-               long long gi_dir_stride) {
+gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int h_stride) {
   constexpr int NC = H / 32, KS = H / 8, BC = 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -140,7 +143,7 @@ gru_bwd_kernel(const float* __restrict__ dh_out, long long h_dir_off, int h_stri
   float* dg = smem;                            // [2][3][BC][H]
   float* red = smem + 2 * 3 * BC * H;          // [8][BC][32]
 
-  const float* w = w_hh + (long long)d * 3 * H * H;
+  const float* w = dirs.w_hh[d];
   float Wt[3][KS];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
@@ -148,11 +151,11 @@ gru_bwd_kernel(const float* __restrict__ dh_out, long long h_dir_off, int h_stri
     for (int kk = 0; kk < KS; ++kk) Wt[g][kk] = __ldg(w + (long long)(g * H + q * KS + kk) * H + u);
 
   const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
-  const float* dho_b = dh_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
-  const float* ho_b = h_out + (long long)d * h_dir_off + (long long)bq * T * h_stride;
-  const float* sv_b = save + ((long long)d * B + bq) * T * 4 * H;
-  float* dgi_b = dgi + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
-  float* dgh_b = dgh + (long long)d * gi_dir_stride + (long long)bq * T * 3 * H;
+  const float* dho_b = dirs.dh_out[d] + (long long)bq * T * h_stride;
+  const float* ho_b = dirs.h_out[d] + (long long)bq * T * h_stride;
+  const float* sv_b = dirs.save[d] + (long long)bq * T * 4 * H;
+  float* dgi_b = dirs.dgi[d] + (long long)bq * T * 3 * H;
+  float* dgh_b = dirs.dgh[d] + (long long)bq * T * 3 * H;
   float dh_carry = 0.f;
   cluster.sync();
 
@@ -218,36 +221,16 @@ gru_bwd_kernel(const float* __restrict__ dh_out, long long h_dir_off, int h_stri
 }
 
 // ------------------------------------------------------------------ launchers
-template <int H>
-static int launch_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh,
-                          const float* b_hh, const int* seq_len, int B, int T, int ndir,
-                          const GruDirs& dirs, float* h_out, long long h_dir_off, int h_stride,
-                          float* save, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(H / 32, cdiv(B, 8), ndir);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_fwd_kernel<H>, gi, gi_dir_stride, w_hh, b_hh, seq_len,
-                                     B, T, dirs, h_out, h_dir_off, h_stride, save);
-  ++g_pbsed_launches;
-  if (e != cudaSuccess) return (int)e;
-  e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : (int)e;
-}
-
-template <int H>
-static int launch_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride, const float* h_out,
-                          const float* save, const float* w_hh, const int* seq_len, int B, int T,
-                          int ndir, const GruDirs& dirs, float* dgi, float* dgh,
-                          long long gi_dir_stride, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * 3 * 8 * H + 8 * 8 * 32) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+template <int H, bool BWD>
+static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs& dirs, int h_stride,
+                      cudaStream_t st) {
+  size_t smem = 0;
+  cudaError_t e;
+  if (BWD) {
+    smem = (size_t)(2 * 3 * 8 * H + 8 * 8 * 32) * sizeof(float);
+    e = cudaFuncSetAttribute(gru_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(H / 32, cdiv(B, 8), ndir);
   cfg.blockDim = dim3(256);
@@ -257,51 +240,55 @@ static int launch_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, gru_bwd_kernel<H>, dh_out, h_dir_off, h_stride, h_out, save, w_hh,
-                         seq_len, B, T, dirs, dgi, dgh, gi_dir_stride);
+  if (BWD) e = cudaLaunchKernelEx(&cfg, gru_bwd_kernel<H>, seq_len, B, T, dirs, h_stride);
+  else     e = cudaLaunchKernelEx(&cfg, gru_fwd_kernel<H>, seq_len, B, T, dirs, h_stride);
   ++g_pbsed_launches;
   if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-static int make_dirs(int ndir, const int* reverse_host, GruDirs& dirs) {
-  if (ndir < 1 || ndir > 4 || !reverse_host) return PBSED_EINVAL;
-  for (int i = 0; i < 4; ++i) dirs.reverse[i] = i < ndir ? reverse_host[i] : 0;
-  return 0;
-}
-
-extern "C" int pbsed_gru_fwd(const float* gi, long long gi_dir_stride, const float* w_hh,
-                             const float* b_hh, const int* seq_len, int B, int T, int H, int ndir,
-                             const int* reverse_host, float* h_out, long long h_dir_off,
-                             int h_stride, float* save, void* stream) {
-  GruDirs dirs;
-  if (make_dirs(ndir, reverse_host, dirs)) return PBSED_EINVAL;
-  if (!gi || !w_hh || !b_hh || !h_out || B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
+template <bool BWD>
+static int dispatch_gru(const int* seq_len, int B, int T, int H, int ndir, const GruDirs& dirs,
+                        int h_stride, cudaStream_t st) {
   switch (H) {
-    case 32:  return launch_gru_fwd<32>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
-    case 64:  return launch_gru_fwd<64>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
-    case 128: return launch_gru_fwd<128>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
-    case 256: return launch_gru_fwd<256>(gi, gi_dir_stride, w_hh, b_hh, seq_len, B, T, ndir, dirs, h_out, h_dir_off, h_stride, save, st);
+    case 32:  return launch_gru<32, BWD>(seq_len, B, T, ndir, dirs, h_stride, st);
+    case 64:  return launch_gru<64, BWD>(seq_len, B, T, ndir, dirs, h_stride, st);
+    case 128: return launch_gru<128, BWD>(seq_len, B, T, ndir, dirs, h_stride, st);
+    case 256: return launch_gru<256, BWD>(seq_len, B, T, ndir, dirs, h_stride, st);
     default:  return PBSED_EINVAL;
   }
 }
 
-extern "C" int pbsed_gru_bwd(const float* dh_out, long long h_dir_off, int h_stride,
-                             const float* h_out, const float* save, const float* w_hh,
+extern "C" int pbsed_gru_fwd(const float* const* gi, const float* const* w_hh,
+                             const float* const* b_hh, const int* seq_len, int B, int T, int H,
+                             int ndir, const int* reverse_host, float* const* h_out, int h_stride,
+                             float* const* save, void* stream) {
+  if (ndir < 1 || ndir > 4 || !reverse_host || !gi || !w_hh || !b_hh || !h_out) return PBSED_EINVAL;
+  if (B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
+  GruDirs dirs = {};
+  for (int d = 0; d < ndir; ++d) {
+    if (!gi[d] || !w_hh[d] || !b_hh[d] || !h_out[d]) return PBSED_EINVAL;
+    dirs.reverse[d] = reverse_host[d];
+    dirs.gi[d] = gi[d]; dirs.w_hh[d] = w_hh[d]; dirs.b_hh[d] = b_hh[d];
+    dirs.h_out[d] = h_out[d]; dirs.save[d] = save ? save[d] : nullptr;
+  }
+  return dispatch_gru<false>(seq_len, B, T, H, ndir, dirs, h_stride, (cudaStream_t)stream);
+}
+
+extern "C" int pbsed_gru_bwd(const float* const* dh_out, const float* const* h_out,
+                             const float* const* save, const float* const* w_hh,
                              const int* seq_len, int B, int T, int H, int ndir,
-                             const int* reverse_host, float* dgi, float* dgh,
-                             long long gi_dir_stride, void* stream) {
-  GruDirs dirs;
-  if (make_dirs(ndir, reverse_host, dirs)) return PBSED_EINVAL;
-  if (!dh_out || !h_out || !save || !w_hh || !dgi || !dgh || B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (H) {
-    case 32:  return launch_gru_bwd<32>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
-    case 64:  return launch_gru_bwd<64>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
-    case 128: return launch_gru_bwd<128>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
-    case 256: return launch_gru_bwd<256>(dh_out, h_dir_off, h_stride, h_out, save, w_hh, seq_len, B, T, ndir, dirs, dgi, dgh, gi_dir_stride, st);
-    default:  return PBSED_EINVAL;
+                             const int* reverse_host, float* const* dgi, float* const* dgh,
+                             int h_stride, void* stream) {
+  if (ndir < 1 || ndir > 4 || !reverse_host || !dh_out || !h_out || !save || !w_hh || !dgi || !dgh) return PBSED_EINVAL;
+  if (B < 1 || T < 1 || h_stride < H) return PBSED_EINVAL;
+  GruDirs dirs = {};
+  for (int d = 0; d < ndir; ++d) {
+    if (!dh_out[d] || !h_out[d] || !save[d] || !w_hh[d] || !dgi[d] || !dgh[d]) return PBSED_EINVAL;
+    dirs.reverse[d] = reverse_host[d];
+    dirs.dh_out[d] = dh_out[d]; dirs.h_out[d] = const_cast<float*>(h_out[d]); dirs.save[d] = const_cast<float*>(save[d]);
+    dirs.w_hh[d] = w_hh[d]; dirs.dgi[d] = dgi[d]; dirs.dgh[d] = dgh[d];
   }
+  return dispatch_gru<true>(seq_len, B, T, H, ndir, dirs, h_stride, (cudaStream_t)stream);
 }

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..modules import CNN, GRU, NormalizedLogMelExtractor, TakeLast, compute_mask
+from ..modules import CNN, GRU, NormalizedLogMelExtractor, TakeLast, compute_mask, gru_stack
 from ..ops import SeqLen, to_native, from_native
 from . import base
 
@@ -71,15 +71,31 @@ class CRNN(base.SoundEventModel):
 
     def forward(self, inputs):
         h, seq, x, seq_len_x, targets = self.encode(inputs, pop=self.training)
-        y_fwd, z = self._scores_native(self.rnn_fwd, h, seq)
-        self._z_fwd = z.detach()              # frame logits (B,T,K), kept for the parity metric
         y_bwd = None
-        if self.rnn_bwd is not None:
-            y_bwd, z = self._scores_native(self.rnn_bwd, h, seq)
-            self._z_bwd = z.detach()
+        if self._can_pair():
+            # both recurrences advance in the same persistent-kernel launches
+            hf, hb = gru_stack([self.rnn_fwd.rnn, self.rnn_bwd.rnn], [h, h], seq,
+                               [self.rnn_fwd.reverse, self.rnn_bwd.reverse])
+            z = self.rnn_fwd.output_net.forward_native(hf.unsqueeze(1), seq).squeeze(1)
+            y_fwd, self._z_fwd = ops.SigmoidScoresFn.apply(z, self.minimum_score), z.detach()
+            z = self.rnn_bwd.output_net.forward_native(hb.unsqueeze(1), seq).squeeze(1)
+            y_bwd, self._z_bwd = ops.SigmoidScoresFn.apply(z, self.minimum_score), z.detach()
+        else:
+            y_fwd, z = self._scores_native(self.rnn_fwd, h, seq)
+            self._z_fwd = z.detach()          # frame logits (B,T,K), kept for the parity metric
+            if self.rnn_bwd is not None:
+                y_bwd, z = self._scores_native(self.rnn_bwd, h, seq)
+                self._z_bwd = z.detach()
         if seq_len_x is None:
             seq_len_x = np.full(x.shape[0], x.shape[-1])
         return y_fwd, y_bwd, seq_len_x, x, seq_len_x, targets
+
+    def _can_pair(self):
+        a, b = self.rnn_fwd, self.rnn_bwd
+        return (isinstance(a, GRU) and isinstance(b, GRU) and a.rnn is not None and b.rnn is not None
+                and not a.rnn.bidirectional and not b.rnn.bidirectional
+                and (a.rnn.hidden_size, a.rnn.num_layers, a.rnn.input_size) ==
+                    (b.rnn.hidden_size, b.rnn.num_layers, b.rnn.input_size))
 
     def read_targets(self, inputs, subsample_idx=None):
         if 'boundary_targets' in inputs:

@@ -471,13 +471,28 @@ class GRUCore(nn.Module):
                     elif strict:
                         missing_keys.append(key)
 
+    def layer_params(self, l):
+        return tuple(getattr(self, f'{n}_{l}') for n in ('w_ih', 'w_hh', 'b_ih', 'b_hh'))
+
     def forward_native(self, x, seq, reverse=False):
         """x (B,T,In) -> (B,T,H*ndir)."""
-        rev = [False, True] if self.bidirectional else [bool(reverse)]
-        for l in range(self.num_layers):
-            x = ops.GruLayerFn.apply(x, getattr(self, f'w_ih_{l}'), getattr(self, f'w_hh_{l}'),
-                                     getattr(self, f'b_ih_{l}'), getattr(self, f'b_hh_{l}'), seq, rev)
-        return x
+        return gru_stack([self], [x], seq, [reverse])[0]
+
+
+def gru_stack(cores, xs, seq, reverses):
+    """run several GRUCore modules of identical shape side by side: every layer is ONE launch that
+    advances all of them concurrently (the reference runs rnn_fwd and rnn_bwd back to back)."""
+    c0 = cores[0]
+    assert all((c.hidden_size, c.num_layers, c.bidirectional) ==
+               (c0.hidden_size, c0.num_layers, c0.bidirectional) for c in cores)
+    meta = [[False, True] if c.bidirectional else [bool(r)] for c, r in zip(cores, reverses)]
+    xs = list(xs)
+    for l in range(c0.num_layers):
+        flat = []
+        for c, x in zip(cores, xs):
+            flat += [x, *c.layer_params(l)]
+        xs = list(ops.GruMultiFn.apply(seq, meta, *flat))
+    return xs
 
 
 class GRU(nn.Module):

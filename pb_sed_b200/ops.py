@@ -255,62 +255,103 @@ class ConvLayerFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------ GRU layer
-class GruLayerFn(torch.autograd.Function):
-    """one GRU layer, ``ndir`` directions.  x (B,T,In) native; weights stacked per direction:
-    w_ih (ndir,3H,In), w_hh (ndir,3H,H), b_ih/b_hh (ndir,3H).  Returns (B,T,ndir*H)."""
+def _ptr_array(tensors_or_ptrs):
+    vals = [(t if isinstance(t, int) else (0 if t is None else t.data_ptr())) for t in tensors_or_ptrs]
+    return (ctypes.c_void_p * len(vals))(*vals)
+
+
+class GruMultiFn(torch.autograd.Function):
+    """ONE layer of G independent GRU modules ("groups"), each with ``nd`` directions, in a single
+    persistent-kernel launch (G*nd <= 4 recurrences run concurrently on disjoint SM clusters).
+
+    apply(seq, meta, *tensors):  meta = [reverse flags per group], tensors = per group
+    (x (B,T,In), w_ih (nd,3H,In), w_hh (nd,3H,H), b_ih (nd,3H), b_hh (nd,3H)).
+    Returns one (B,T,nd*H) map per group.  The reference's rnn_fwd / rnn_bwd pair
+    (weak_label/crnn.py:338-340) is G = 2, nd = 1; its bidirectional GRU (strong_label/crnn.py:
+    189-195) is G = 1, nd = 2.
+    """
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, seq, reverse):
-        x = _f32c(x)
-        B, T, In = x.shape
-        ndir, H3, H = w_hh.shape
-        gi = torch.empty((ndir, B, T, H3), device=x.device)
-        for d in range(ndir):
-            desc = make_desc(B, 1, 1, T, In, H3, [(0, 0)])
-            tapgemm(x, w_ih[d], b_ih[d], desc, seq=seq, out=gi[d])
-        h = torch.empty((B, T, ndir * H), device=x.device)
-        save = torch.empty((ndir, B, T, 4 * H), device=x.device)
-        rev = (ctypes.c_int * 4)(*([int(r) for r in reverse] + [0] * (4 - ndir)))
-        call('pbsed_gru_fwd', _ptr(gi), B * T * H3, _ptr(w_hh), _ptr(b_hh), seq.ptr, B, T, H, ndir,
-             rev, _ptr(h), H, ndir * H, _ptr(save), _stream())
-        ctx.seq, ctx.reverse = seq, list(reverse)
-        ctx.save_for_backward(x, w_ih, w_hh, h, save)
-        ctx.params = (w_ih, w_hh, b_ih, b_hh)
-        return h
+    def forward(ctx, seq, meta, *tensors):
+        G = len(meta)
+        groups = [tensors[5 * g:5 * g + 5] for g in range(G)]
+        x0 = groups[0][0]
+        B, T, _ = x0.shape
+        nd, H3, H = groups[0][2].shape
+        dev = x0.device
+        gis, hs, saves, xs = [], [], [], []
+        p_gi, p_whh, p_bhh, p_h, p_save, rev = [], [], [], [], [], []
+        for g in range(G):
+            x, w_ih, w_hh, b_ih, b_hh = groups[g]
+            x = _f32c(x)
+            xs.append(x)
+            assert w_hh.shape == (nd, H3, H) and x.shape[:2] == (B, T)
+            In = x.shape[2]
+            gi = torch.empty((nd, B, T, H3), device=dev)
+            for d in range(nd):
+                tapgemm(x, w_ih[d], b_ih[d], make_desc(B, 1, 1, T, In, H3, [(0, 0)]), seq=None, out=gi[d])
+            h = torch.empty((B, T, nd * H), device=dev)
+            save = torch.empty((nd, B, T, 4 * H), device=dev)
+            gis.append(gi); hs.append(h); saves.append(save)
+            for d in range(nd):
+                p_gi.append(gi[d]); p_whh.append(w_hh[d]); p_bhh.append(b_hh[d])
+                p_h.append(h.data_ptr() + 4 * d * H); p_save.append(save[d])
+                rev.append(int(meta[g][d]))
+        n = len(rev)
+        call('pbsed_gru_fwd', _ptr_array(p_gi), _ptr_array(p_whh), _ptr_array(p_bhh), seq.ptr, B, T, H,
+             n, (ctypes.c_int * n)(*rev), _ptr_array(p_h), nd * H, _ptr_array(p_save), _stream())
+        ctx.seq, ctx.meta, ctx.rev, ctx.dims = seq, meta, rev, (G, nd, B, T, H)
+        ctx.save_for_backward(*xs, *hs, *saves, *[groups[g][1] for g in range(G)],
+                              *[groups[g][2] for g in range(G)])
+        ctx.params = [groups[g][1:] for g in range(G)]
+        return tuple(hs)
 
     @staticmethod
-    def backward(ctx, dh):
-        x, w_ih, w_hh, h, save = ctx.saved_tensors
-        p_wih, p_whh, p_bih, p_bhh = ctx.params
-        seq, reverse = ctx.seq, ctx.reverse
-        B, T, In = x.shape
-        ndir, H3, H = w_hh.shape
-        dh = _f32c(dh)
-        dgi = torch.empty((ndir, B, T, H3), device=x.device)
-        dgh = torch.empty((ndir, B, T, H3), device=x.device)
-        rev = (ctypes.c_int * 4)(*([int(r) for r in reverse] + [0] * (4 - ndir)))
-        call('pbsed_gru_bwd', _ptr(dh), H, ndir * H, _ptr(h), _ptr(save), _ptr(w_hh), seq.ptr, B, T,
-             H, ndir, rev, _ptr(dgi), _ptr(dgh), B * T * H3, _stream())
-        dwih, r0 = _grad_target(p_wih)
-        dwhh, r1 = _grad_target(p_whh)
-        dbih, r2 = _grad_target(p_bih)
-        dbhh, r3 = _grad_target(p_bhh)
-        dx = None
-        for d in range(ndir):
-            if dwih is not None:
-                desc = make_desc(B, 1, 1, T, In, H3, [(0, 0)])
-                tapgemm_wgrad(x, dgi[d], desc, dwih[d], dbih[d] if dbih is not None else None,
-                              seq=seq, mask_out=True)
-            if dwhh is not None:
-                desc = make_desc(B, 1, 1, T, H, H3, [(0, 1 if reverse[d] else -1)], in_stride=ndir * H)
-                tapgemm_wgrad(None, dgh[d], desc, dwhh[d], dbhh[d] if dbhh is not None else None,
-                              seq=seq, mask_out=True,
-                              x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * d * H))
-            if ctx.needs_input_grad[0]:
-                ddesc = make_desc(B, 1, 1, T, H3, In, [(0, 0)], transpose_w=True)
-                g = tapgemm(dgi[d], w_ih[d], None, ddesc, seq=seq).view(B, T, In)
-                dx = g if dx is None else dx.add_(g)
-        return dx, r0, r1, r2, r3, None, None
+    def backward(ctx, *dhs):
+        G, nd, B, T, H = ctx.dims
+        H3 = 3 * H
+        sv = ctx.saved_tensors
+        xs, hs, saves = sv[0:G], sv[G:2 * G], sv[2 * G:3 * G]
+        w_ihs, w_hhs = sv[3 * G:4 * G], sv[4 * G:5 * G]
+        seq, rev = ctx.seq, ctx.rev
+        dev = xs[0].device
+        dgis = [torch.empty((nd, B, T, H3), device=dev) for _ in range(G)]
+        dghs = [torch.empty((nd, B, T, H3), device=dev) for _ in range(G)]
+        dhs = [(_f32c(dh) if dh is not None else torch.zeros((B, T, nd * H), device=dev)) for dh in dhs]
+        p_dh, p_h, p_save, p_whh, p_dgi, p_dgh = [], [], [], [], [], []
+        for g in range(G):
+            for d in range(nd):
+                p_dh.append(dhs[g].data_ptr() + 4 * d * H); p_h.append(hs[g].data_ptr() + 4 * d * H)
+                p_save.append(saves[g][d]); p_whh.append(w_hhs[g][d])
+                p_dgi.append(dgis[g][d]); p_dgh.append(dghs[g][d])
+        n = G * nd
+        call('pbsed_gru_bwd', _ptr_array(p_dh), _ptr_array(p_h), _ptr_array(p_save), _ptr_array(p_whh),
+             seq.ptr, B, T, H, n, (ctypes.c_int * n)(*rev), _ptr_array(p_dgi), _ptr_array(p_dgh),
+             nd * H, _stream())
+        grads = []
+        for g in range(G):
+            p_wih, p_whh_, p_bih, p_bhh = ctx.params[g]
+            x, h = xs[g], hs[g]
+            In = x.shape[2]
+            dwih, r0 = _grad_target(p_wih)
+            dwhh, r1 = _grad_target(p_whh_)
+            dbih, r2 = _grad_target(p_bih)
+            dbhh, r3 = _grad_target(p_bhh)
+            dx = None
+            for d in range(nd):
+                if dwih is not None:
+                    tapgemm_wgrad(x, dgis[g][d], make_desc(B, 1, 1, T, In, H3, [(0, 0)]), dwih[d],
+                                  dbih[d] if dbih is not None else None, seq=seq, mask_out=True)
+                if dwhh is not None:
+                    desc = make_desc(B, 1, 1, T, H, H3, [(0, 1 if rev[g * nd + d] else -1)], in_stride=nd * H)
+                    tapgemm_wgrad(None, dghs[g][d], desc, dwhh[d], dbhh[d] if dbhh is not None else None,
+                                  seq=seq, mask_out=True, x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * d * H))
+                if ctx.needs_input_grad[2 + 5 * g]:
+                    ddesc = make_desc(B, 1, 1, T, H3, In, [(0, 0)], transpose_w=True)
+                    gx = tapgemm(dgis[g][d], w_ihs[g][d], None, ddesc, seq=None).view(B, T, In)
+                    dx = gx if dx is None else dx.add_(gx)
+            grads += [dx, r0, r1, r2, r3]
+        return (None, None, *grads)
 
 
 # ------------------------------------------------------------------ misc element-wise ops

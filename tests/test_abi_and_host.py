@@ -27,7 +27,7 @@ def test_bad_arguments_return_einval_without_touching_the_gpu(built_lib):
     d.B = d.F_in = d.F_out = d.T = d.Cin = d.Cout = 1
     d.ntaps = 99
     assert built_lib.pbsed_tapgemm_wgrad(ctypes.byref(d), None, None, None, None, None, 0, None, None, None) == -1
-    assert built_lib.pbsed_gru_fwd(None, 0, None, None, None, 1, 1, 48, 1, None, None, 0, 48, None, None) == -1
+    assert built_lib.pbsed_gru_fwd(None, None, None, None, 1, 1, 48, 1, None, None, 48, None, None) == -1
     assert built_lib.pbsed_stft_logmel(None, 1, 1, 1, 1, 8, 0, 1, None, None, None, None, 1, 1, None, None, None, None) == -1
     with pytest.raises(_lib.PbsedError):
         _lib.call('pbsed_adam_step', None, None, None, None, 0, None, None, None, 0, None)
