@@ -25,6 +25,21 @@ from ._lib import call
 from .ops import _ptr, _stream
 
 
+def allreduce_flat(flat, group=None):
+    """sum-all-reduce one flat gradient buffer in place (NCCL on GPUs; gloo in the CPU tests).
+    The 1/world scaling is folded into the fused Adam kernel (``hyper[6]``)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def shard_bounds(n_items, rank, world):
+    """contiguous, balanced shard [lo, hi) of ``n_items`` clips for ``rank``."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class FlatArena:
     def __init__(self, module):
         params = [p for p in module.parameters() if p.requires_grad]
@@ -86,7 +101,7 @@ class Adam:
 
     def allreduce_grads(self):
         if self.distributed:
-            dist.all_reduce(self.arena.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+            allreduce_flat(self.arena.grads, self.process_group)
 
     def step(self):
         """all-reduce (if DP) -> global norm -> clip -> Adam -> zero the gradient arena."""
