@@ -163,6 +163,21 @@ def kernel_breakdown(model, opt, batch, train, _lib):
     _lib.profile_sink = None
     torch.cuda.synchronize()
     agg = {}
+    detail = []
+    for name, e0, e1, a in sink:
+        ms = e0.elapsed_time(e1)
+        key = name
+        if name in ('pbsed_tapgemm', 'pbsed_tapgemm_wgrad'):
+            d = a[0]._obj
+            detail.append((name, f'B{d.B} F{d.F_in}>{d.F_out} T{d.T} C{d.Cin}>{d.Cout} taps{d.ntaps} '
+                                 f'relu{d.relu} ws{d.w_sn}', round(ms, 3),
+                           round(tapgemm_flops(a) / (ms / 1e3) / 1e12, 1)))
+        else:
+            detail.append((name, '', round(ms, 3), None))
+    if os.environ.get('PBSED_BENCH_DETAIL'):
+        with open(os.environ['PBSED_BENCH_DETAIL'], 'w') as f:
+            for row in detail:
+                f.write(' '.join(str(x) for x in row) + '\n')
     for name, e0, e1, a in sink:
         ms = e0.elapsed_time(e1)
         key = name

@@ -107,7 +107,10 @@ int pbsed_tapgemm(const pbsed_tapgemm_desc* d_host,
                   const float* in, const float* scale, const float* shift, const int* seq_len,
                   const float* W, const float* bias, float* out,
                   const float* ep_src, const float* ep_scale, const float* ep_shift,
-                  void* stream);
+                  void* workspace, long long workspace_bytes, void* stream);
+/* bytes of caller-owned scratch the tensor-core path needs (pre-tiled hi/lo weight image);
+ * 0 for precision 0.  A NULL / too small workspace with precision != 0 runs the exact-fp32 kernel. */
+long long pbsed_tapgemm_workspace_bytes(const pbsed_tapgemm_desc* d_host);
 
 /* weight gradient of the same contraction:
  *   dW[tap][n][c] += sum_{b,fo,t}  dout[(b,fo,t), n] * a[(b, fo+df, t+dt), c]       (a as above)

@@ -211,12 +211,14 @@ static int launch_fwd(const TapParams& p, const float* in, const float* scale, c
 int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                         const float* shift, const int* seq_len, const float* W, const float* bias,
                         float* out, const float* ep_src, const float* ep_scale,
-                        const float* ep_shift, cudaStream_t st, int* handled);
+                        const float* ep_shift, void* workspace, long long ws_bytes,
+                        cudaStream_t st, int* handled);
 
 extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                              const float* shift, const int* seq_len, const float* W,
                              const float* bias, float* out, const float* ep_src,
-                             const float* ep_scale, const float* ep_shift, void* stream) {
+                             const float* ep_scale, const float* ep_shift, void* workspace,
+                             long long workspace_bytes, void* stream) {
   TapParams p;
   int rc = fill_params(d, p);
   if (rc) return rc;
@@ -226,8 +228,8 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   if (d->precision != 0) {
     int handled = 0;
     rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
-                             st, &handled);
-    if (handled) return rc;
+                             workspace, workspace_bytes, st, &handled);
+    if (handled || rc) return rc;
   }
   if (p.Cout <= 16)
     return launch_fwd<128, 16, 16, 8, 2>(p, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);

@@ -1,14 +1,446 @@
-// tapgemm_tc.cu -- tcgen05 (5th-gen tensor core) tap-GEMM for channel counts that fill UMMA tiles.
-// precision 1 = 3xTF32 split (fp32-equivalent accuracy), 2 = bf16.   [under construction: returns
-// handled = 0 so that pbsed_tapgemm runs the exact-fp32 FFMA kernel]
+// tapgemm_tc.cu -- tcgen05 (5th-gen tensor core) tap-GEMM for sm_100a.
+//
+// Same contraction as tapgemm.cu (padertorch CNN2d / CNN1d layer bodies, GRU projections,
+// output_net; pb_sed/experiments/weak_label_crnn/training.py:218-260), on the tensor cores:
+//
+//   precision 1: 3xTF32 split -- a = a_hi + a_lo, w = w_hi + w_lo (10-bit mantissa pieces),
+//                acc += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (kind::tf32, fp32 accumulation in TMEM)
+//                => fp32-equivalent accuracy (one TF32 pass misses the 1e-3
+//                frame-logit bar by 40x, the split meets it with 30x margin)
+//
+// CTA = one (b, fo) row group x up to 512 frames (4 row tiles of 128) x a slice of N <= 128 output
+// channels.  Accumulators: 4 x N fp32 columns of TMEM.  Warp roles:
+//   warps 0-3  A producers: load the source strip (f+df) of 512+2 frames x 16 channels, apply
+//              norm scale/shift + ReLU + sequence mask, split hi/lo, store K-major with a uniform
+//              16-byte row pitch  [k-chunk][frame][4 floats]  -- so the dt = -1/0/+1 taps are the
+//              SAME buffer addressed with a +-16-byte descriptor offset (3 strip loads feed 9 taps).
+//              After the main loop the same warps run the epilogue (TMEM -> registers -> bias /
+//              ReLU-mask -> global).
+//   warp 4     lane 0 issues tcgen05.mma (M128 x N x K8) and tcgen05.commit; the warp owns TMEM.
+//   warp 5     lane 0 streams the pre-tiled weight images with 1-D bulk copies (cp.async.bulk ->
+//              UBLKCP) onto mbarriers.
+// Operand layouts are the canonical UMMA K-major SWIZZLE_NONE ("interleave") form:
+//   byte(row r, 16-byte k-chunk c) = c*LBO + (r/8)*SBO + (r%8)*16   with SBO = 128  => row pitch 16.
 #include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int MT_MAX = 4;            // row tiles per CTA
+constexpr int KB = 16;               // channels per pipeline stage (two K=8 tf32 MMA steps)
+constexpr int KCH = KB / 4;          // 16-byte chunks per stage
+constexpr int NA = 2, NB = 4;        // A / B ring depths
+constexpr int HALO = 1;
+// strip rows R = MT*128 + 2: R*4 words == 8 (mod 32), so the four 16-byte k-chunks of a frame land in
+// disjoint bank groups and the producer's (frame, chunk)-ordered float4 stores are conflict-free
+constexpr int NSLICE = 128;
+constexpr int MAXG = PBSED_MAX_TAPS;
+
+struct TcParams {
+  int B, F_in, F_out, T, Cin, Cout;
+  int relu, per_f;
+  int in_stride, out_stride;
+  int N;                 // channels per CTA slice
+  int n_slices, nkb, ntaps;
+  int ngroups;           // taps grouped by df
+  int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2)
+// [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ weight image
+// image[slice][tap][kb] = { part hi | part lo } x [k-chunk (4)][n (N)][4 floats]
+__global__ void __launch_bounds__(256)
+wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
+             int ntaps, int Cin, int Cout, int N, float* __restrict__ img) {
+  const int nkb = Cin / KB, n_slices = Cout / N;
+  const long long total = (long long)n_slices * ntaps * nkb * KCH * N * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int e = (int)(i & 3);
+    long long q = i >> 2;
+    const int n = (int)(q % N); q /= N;
+    const int c = (int)(q % KCH); q /= KCH;
+    const int kb = (int)(q % nkb); q /= nkb;
+    const int tap = (int)(q % ntaps);
+    const int sl = (int)(q / ntaps);
+    const int cin = kb * KB + c * 4 + e, cout = sl * N + n;
+    const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)cout * w_sn + (long long)cin * w_sc);
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const long long blob = ((long long)(sl * ntaps + tap) * nkb + kb) * (2LL * KCH * N * 4);
+    const long long off = ((long long)c * N + n) * 4 + e;
+    img[blob + off] = hi;
+    img[blob + (long long)KCH * N * 4 + off] = w - hi;
+  }
+}
+
+// ------------------------------------------------------------------ main kernel
+struct __align__(16) SmemCtl {
+  uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], acc_full;
+  uint32_t tmem_base;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(192)
+tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const int* __restrict__ seq_len,
+                  const float* __restrict__ img, const float* __restrict__ bias,
+                  float* __restrict__ out, const float* __restrict__ ep_src,
+                  const float* __restrict__ ep_scale, const float* __restrict__ ep_shift,
+                  int t_super) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int N = p.N;
+  constexpr int RMAX = MT * TILE_M + 2 * HALO;         // strip rows
+  constexpr uint32_t A_PART = KCH * RMAX * 16;         // bytes of one hi (or lo) strip stage
+  constexpr uint32_t A_STAGE = 2 * A_PART;
+  const uint32_t B_PART = KCH * N * 16;
+  const uint32_t B_STAGE = 2 * B_PART;
+  uint8_t* a_smem = smem_raw;
+  uint8_t* b_smem = smem_raw + NA * A_STAGE;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(b_smem + NB * B_STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x % p.n_slices, st = blockIdx.x / p.n_slices;
+  const int fo = blockIdx.y, b = blockIdx.z;
+  const int t0 = st * (MT * TILE_M);
+  const int rows_here = min(p.T - t0, MT * TILE_M);
+  const int mt_count = (rows_here + TILE_M - 1) / TILE_M;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < mt_count * N) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
+    mbar_init(&ctl->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  // the stage list is identical for every role: (kb, group g) with a valid source row f = fo + df
+  if (warp < 4) {
+    // ============================== A producer ==============================
+    int it = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int f_src = fo + p.g_df[g];
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int slot = it % NA;
+        mbar_wait(&ctl->a_empty[slot], ((it / NA) & 1) ^ 1);
+        uint8_t* hi_base = a_smem + slot * A_STAGE;
+        uint8_t* lo_base = hi_base + A_PART;
+        const long long row0 = ((long long)b * p.F_in + f_src) * p.T;
+        const int c = tid & 3;                       // this thread's 16-byte k-chunk (idx & 3 is invariant)
+        const float* src = in + row0 * p.in_stride + kb * KB + c * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (scale) {
+          const int aff = (p.per_f ? f_src * p.Cin : 0) + kb * KB + c * 4;
+          sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
+          sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+        }
+        const int nrows = mt_count * TILE_M + 2 * HALO;
+        constexpr int U = 8;                         // independent 16-byte loads in flight per thread
+        for (int r0 = tid >> 2; r0 < nrows; r0 += 32 * U) {
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = r0 + 32 * u, t = t0 + r - HALO;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows && t >= 0 && t < len_b)
+              v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * p.in_stride));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = r0 + 32 * u, t = t0 + r - HALO;
+            if (r >= nrows) break;
+            float4 x = v[u];
+            if (t >= 0 && t < len_b) {
+              if (scale) {
+                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+              }
+              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            const uint32_t o = (uint32_t)(c * RMAX + r) * 16;
+            *reinterpret_cast<float4*>(hi_base + o) = h;
+            *reinterpret_cast<float4*>(lo_base + o) = l;
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(&ctl->a_full[slot]);
+        ++it;
+      }
+    }
+    // ============================== epilogue ==============================
+    mbar_wait(&ctl->acc_full, 0);
+    tc_fence_after();
+    const long long orow0 = ((long long)b * p.F_out + fo) * p.T;
+    const int n0 = slice * N;
+    const int ep_base = (p.per_f ? fo * p.Cout : 0) + n0;
+    for (int mt = 0; mt < mt_count; ++mt) {
+      const int t = t0 + mt * TILE_M + warp * 32 + lane;
+      for (int cc = 0; cc < N; cc += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + cc), v);
+        if (t < p.T) {
+          float* dst = out + (orow0 + t) * p.out_stride + n0 + cc;
+          const float* es = ep_src ? ep_src + (orow0 + t) * p.out_stride + n0 + cc : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (es) {
+              float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t < len_b) {
+                s = __ldg(reinterpret_cast<const float4*>(es + j));
+                if (ep_scale) {
+                  const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
+                  const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
+                  s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
+                  s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
+                }
+              }
+              o.x = s.x > 0.f ? o.x : 0.f; o.y = s.y > 0.f ? o.y : 0.f;
+              o.z = s.z > 0.f ? o.z : 0.f; o.w = s.w > 0.f ? o.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TILE_M, N);
+      const uint32_t a_lbo = RMAX * 16, b_lbo = (uint32_t)N * 16;
+      int it = 0, bt = 0;
+      bool first = true;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int f_src = fo + p.g_df[g];
+          if (f_src < 0 || f_src >= p.F_in) continue;
+          const int slot = it % NA;
+          mbar_wait(&ctl->a_full[slot], (it / NA) & 1);
+          const uint32_t a_hi = smem_u32(a_smem + slot * A_STAGE), a_lo = a_hi + A_PART;
+          for (int j = 0; j < p.g_n[g]; ++j) {
+            const int bslot = bt % NB;
+            mbar_wait(&ctl->b_full[bslot], (bt / NB) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(b_smem + bslot * B_STAGE), b_lo = b_hi + B_PART;
+            const int dt = p.g_dt[g][j];
+            for (int mt = 0; mt < mt_count; ++mt) {
+              const uint32_t d = tmem_base + (uint32_t)(mt * N);
+              const uint32_t arow = (uint32_t)(mt * TILE_M + dt + HALO) * 16;
+#pragma unroll
+              for (int ks = 0; ks < KB / 8; ++ks) {
+                const uint32_t ao = arow + (uint32_t)(ks * 2) * a_lbo, bo = (uint32_t)(ks * 2) * b_lbo;
+                const uint64_t dah = make_desc(a_hi + ao, a_lbo, 128), dal = make_desc(a_lo + ao, a_lbo, 128);
+                const uint64_t dbh = make_desc(b_hi + bo, b_lbo, 128), dbl = make_desc(b_lo + bo, b_lbo, 128);
+                mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+                mma_tf32(d, dal, dbh, idesc, 1u);
+                mma_tf32(d, dah, dbl, idesc, 1u);
+              }
+            }
+            first = false;
+            mma_commit(&ctl->b_empty[bslot]);
+            ++bt;
+          }
+          mma_commit(&ctl->a_empty[slot]);
+          ++it;
+        }
+      }
+      mma_commit(&ctl->acc_full);
+    }
+  } else {
+    // ============================== weight loader ==============================
+    if (lane == 0) {
+      int bt = 0;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const int f_src = fo + p.g_df[g];
+          if (f_src < 0 || f_src >= p.F_in) continue;
+          for (int j = 0; j < p.g_n[g]; ++j) {
+            const int bslot = bt % NB;
+            mbar_wait(&ctl->b_empty[bslot], ((bt / NB) & 1) ^ 1);
+            const long long blob = ((long long)(slice * p.ntaps + p.g_tap[g][j]) * p.nkb + kb) * (long long)(B_STAGE / 4);
+            mbar_expect_tx(&ctl->b_full[bslot], B_STAGE);
+            bulk_g2s(b_smem + bslot * B_STAGE, img + blob, B_STAGE, &ctl->b_full[bslot]);
+            ++bt;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// per-row-tile "first" flag: the first MMA into EACH accumulator must overwrite.  The loop above
+// sets accumulate = 0 only while `first` (the very first (kb, group, tap) triple), for every mt.
+
+extern "C" long long pbsed_tapgemm_workspace_bytes(const pbsed_tapgemm_desc* d) {
+  if (!d || d->precision == 0) return 0;
+  return 2LL * d->ntaps * (long long)d->Cin * d->Cout * sizeof(float) + 256;
+}
+
+static bool tc_eligible(const pbsed_tapgemm_desc* d) {
+  if (d->Cin % KB || d->Cout % 16) return false;
+  if (d->Cout > NSLICE && d->Cout % NSLICE) return false;
+  const int in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
+  const int out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+  if (in_stride % 4 || out_stride % 4) return false;
+  for (int i = 0; i < d->ntaps; ++i)
+    if (d->dt[i] < -HALO || d->dt[i] > HALO) return false;
+  return true;
+}
 
 int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                         const float* shift, const int* seq_len, const float* W, const float* bias,
                         float* out, const float* ep_src, const float* ep_scale,
-                        const float* ep_shift, cudaStream_t st, int* handled) {
-  (void)d; (void)in; (void)scale; (void)shift; (void)seq_len; (void)W; (void)bias; (void)out;
-  (void)ep_src; (void)ep_scale; (void)ep_shift; (void)st;
+                        const float* ep_shift, void* workspace, long long ws_bytes,
+                        cudaStream_t st, int* handled) {
   *handled = 0;
-  return 0;
+  if (d->precision != 1 || !workspace || !tc_eligible(d)) return 0;
+  if (ws_bytes < pbsed_tapgemm_workspace_bytes(d)) return PBSED_EWORKSPACE;
+  if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale |
+        (uintptr_t)shift | (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift) & 15) != 0)
+    return 0;                                   // unaligned views: exact-fp32 kernel handles them
+  TcParams p = {};
+  p.B = d->B; p.F_in = d->F_in; p.F_out = d->F_out; p.T = d->T; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.relu = d->relu; p.per_f = d->per_f;
+  p.in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
+  p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+  p.N = d->Cout < NSLICE ? d->Cout : NSLICE;
+  p.n_slices = d->Cout / p.N;
+  p.nkb = d->Cin / KB;
+  p.ntaps = d->ntaps;
+  // group taps by df
+  for (int i = 0; i < d->ntaps; ++i) {
+    int g = 0;
+    for (; g < p.ngroups; ++g)
+      if (p.g_df[g] == d->df[i] && p.g_n[g] < 3) break;
+    if (g == p.ngroups) { p.g_df[g] = d->df[i]; p.g_n[g] = 0; ++p.ngroups; }
+    p.g_tap[g][p.g_n[g]] = i; p.g_dt[g][p.g_n[g]] = d->dt[i]; ++p.g_n[g];
+  }
+  float* img = reinterpret_cast<float*>(workspace);
+  {
+    const long long total = (long long)d->ntaps * d->Cin * d->Cout;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img);
+    int rc = pbsed_after_launch();
+    if (rc) return rc;
+  }
+  // row tiles per CTA: big N wants many rows per weight fetch, small N wants co-resident CTAs
+  int mt = p.N >= 128 ? 4 : (p.N >= 64 ? 2 : 1);
+  while (mt > 1 && (long long)p.B * p.F_out * cdiv(p.T, mt * TILE_M) * p.n_slices < 2 * 148) mt >>= 1;
+  const size_t smem = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)NB * 2 * KCH * p.N * 16 +
+                     sizeof(SmemCtl) + 128;
+  const int t_super = cdiv(p.T, mt * TILE_M);
+  dim3 grid(t_super * p.n_slices, p.F_out, p.B);
+  if (grid.y > 65535 || grid.z > 65535) return 0;
+  cudaError_t e;
+#define PBSED_TC_LAUNCH(MTV)                                                                          \
+  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return (int)e;                                                                 \
+  tapgemm_tc_kernel<MTV><<<grid, 192, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
+                                                  ep_scale, ep_shift, t_super);
+  if (mt == 4) { PBSED_TC_LAUNCH(4) } else if (mt == 2) { PBSED_TC_LAUNCH(2) } else { PBSED_TC_LAUNCH(1) }
+#undef PBSED_TC_LAUNCH
+  *handled = 1;
+  return pbsed_after_launch();
 }

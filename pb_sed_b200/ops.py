@@ -17,8 +17,10 @@ import torch
 from . import _lib
 from ._lib import TapGemmDesc, call
 
+import os
+
 PRECISION = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
-_default_precision = 0
+_default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'fp32')]
 
 
 def set_default_precision(p):
@@ -127,9 +129,13 @@ def tapgemm(x, W, bias, desc, scale=None, shift=None, seq=None, ep_src=None, ep_
     rows = desc.B * desc.F_out * desc.T
     if out is None:
         out = torch.empty((rows, desc.Cout), device=W.device, dtype=torch.float32)
+    ws, ws_bytes = None, 0
+    if desc.precision != 0:
+        ws_bytes = int(_lib.load().pbsed_tapgemm_workspace_bytes(ctypes.byref(desc)))
+        ws = torch.empty(ws_bytes, device=W.device, dtype=torch.uint8)
     call('pbsed_tapgemm', ctypes.byref(desc), x_ptr if x_ptr is not None else _ptr(x), _ptr(scale),
          _ptr(shift), seq.ptr if seq is not None else None, _ptr(W), _ptr(bias), _ptr(out),
-         _ptr(ep_src), _ptr(ep_scale), _ptr(ep_shift), _stream())
+         _ptr(ep_src), _ptr(ep_scale), _ptr(ep_shift), _ptr(ws), ws_bytes, _stream())
     return out
 
 

@@ -80,11 +80,13 @@ def test_conv2d_forward_backward_vs_torch(B, Cin, Cout, Fh, T, k):
     w = conv._to_ref(conv.weight.detach().cpu()).requires_grad_(True)
     b = conv.bias.detach().cpu().clone().requires_grad_(True)
     yr = F.conv2d(F.pad(xr, (1, 1, 1, 1)), w, b)
-    assert reldiff(y.permute(0, 3, 1, 2), yr) < 1e-5          # exact-fp32 FFMA path
+    # exact-fp32 FFMA path: 1e-5; split-TF32 tensor-core path (PBSED_PRECISION=tf32x3): 5e-5
+    tol = 1e-5 if ops._default_precision == 0 else 5e-5
+    assert reldiff(y.permute(0, 3, 1, 2), yr) < tol
     g = torch.randn_like(yr)
     yr.backward(g)
     y.backward(g.permute(0, 2, 3, 1).contiguous().to(DEV))
-    assert reldiff(xg.grad.permute(0, 3, 1, 2), xr.grad) < 1e-5
+    assert reldiff(xg.grad.permute(0, 3, 1, 2), xr.grad) < tol
     assert reldiff(conv._to_ref(conv.weight.grad.cpu()), w.grad) < 1e-4
     assert reldiff(conv.bias.grad, b.grad) < 1e-4
 

@@ -1,0 +1,86 @@
+"""GPU (-m gpu): the tcgen05 (3xTF32) tap-GEMM against the exact-fp32 FFMA kernel on identical inputs.
+Split-TF32 keeps ~21 mantissa bits per product, so the two must agree to ~1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from util import maxdiff, reldiff
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+TAPS_3x3 = [(i - 1, j - 1) for i in range(3) for j in range(3)]
+TAPS_1x3 = [(0, -1), (0, 0), (0, 1)]
+TAPS_1x1 = [(0, 0)]
+
+
+def run(prec, x, W, bias, dims, taps, scale=None, shift=None, relu=False, per_f=False, seq=None,
+        transpose_w=False, ep=None):
+    from pb_sed_b200 import ops
+    B, F_in, F_out, T, Cin, Cout = dims
+    desc = ops.make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=relu, per_f=per_f,
+                         transpose_w=transpose_w, precision=prec)
+    kw = {}
+    if ep is not None:
+        kw = dict(ep_src=ep[0], ep_scale=ep[1], ep_shift=ep[2])
+    return ops.tapgemm(x, W, bias, desc, scale, shift, seq, **kw)
+
+
+@pytest.mark.parametrize('B,F,T,Cin,Cout,taps', [
+    (1, 1, 128, 16, 16, TAPS_1x1),
+    (2, 3, 37, 16, 16, TAPS_3x3),
+    (2, 4, 500, 32, 64, TAPS_3x3),
+    (1, 2, 600, 64, 128, TAPS_3x3),
+    (1, 2, 260, 128, 256, TAPS_3x3),
+    (3, 1, 500, 256, 768, TAPS_1x1),
+    (2, 1, 300, 256, 256, TAPS_1x3),
+])
+def test_tc_forward_matches_ffma(built_lib, B, F, T, Cin, Cout, taps):
+    from pb_sed_b200 import ops
+    torch.manual_seed(Cin + Cout + T)
+    x = torch.randn(B, F, T, Cin, device=DEV)
+    W = torch.randn(len(taps), Cout, Cin, device=DEV) / np.sqrt(Cin * len(taps))
+    bias = torch.randn(Cout, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    sl = np.minimum(np.array([T, max(T - 3, 1), max(T // 2, 1)][:B]), T)
+    seq = ops.SeqLen.make(sl, B, T, DEV)
+    dims = (B, F, F, T, Cin, Cout)
+    for kw in (dict(), dict(scale=scale, shift=shift, relu=True, seq=seq)):
+        ref = run(0, x, W, bias, dims, taps, **kw)
+        out = run(1, x, W, bias, dims, taps, **kw)
+        assert torch.isfinite(out).all()
+        assert reldiff(out, ref) < 2e-5, kw.keys()
+
+
+def test_tc_flatten_conv_per_f_affine(built_lib):
+    """first CNN1d layer: 8 frequency taps over the (B,8,T,256) map, batch norm indexed per (f, c)."""
+    torch.manual_seed(0)
+    B, Fh, T, Cin, Cout = 2, 8, 200, 64, 128
+    taps = [(f, 0) for f in range(Fh)]
+    x = torch.randn(B, Fh, T, Cin, device=DEV)
+    W = torch.randn(len(taps), Cout, Cin, device=DEV) / np.sqrt(Cin * Fh)
+    scale = torch.rand(Fh * Cin, device=DEV) + .5
+    shift = torch.randn(Fh * Cin, device=DEV) * .3
+    dims = (B, Fh, 1, T, Cin, Cout)
+    ref = run(0, x, W, None, dims, taps, scale=scale, shift=shift, relu=True, per_f=True)
+    out = run(1, x, W, None, dims, taps, scale=scale, shift=shift, relu=True, per_f=True)
+    assert reldiff(out, ref) < 2e-5
+
+
+def test_tc_dgrad_with_relu_mask_epilogue(built_lib):
+    from pb_sed_b200 import ops
+    torch.manual_seed(1)
+    B, F, T, Cin, Cout = 2, 3, 300, 32, 64            # forward layer Cin -> Cout
+    dz = torch.randn(B, F, T, Cout, device=DEV)
+    W = torch.randn(9, Cout, Cin, device=DEV) / np.sqrt(Cin * 9)
+    xprev = torch.randn(B, F, T, Cin, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    seq = ops.SeqLen.make(np.array([T, T - 40]), B, T, DEV)
+    rtaps = [(-a, -b) for a, b in TAPS_3x3]
+    dims = (B, F, F, T, Cout, Cin)
+    ref = run(0, dz, W, None, dims, rtaps, seq=seq, transpose_w=True, ep=(xprev, scale, shift))
+    out = run(1, dz, W, None, dims, rtaps, seq=seq, transpose_w=True, ep=(xprev, scale, shift))
+    assert reldiff(out, ref) < 2e-5
+    assert float((out == 0).float().mean()) > .3      # the ReLU mask really zeroed entries
