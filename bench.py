@@ -274,7 +274,7 @@ def run_gpu(args):
         out = {
             'metric': 'fbcrnn_train_clips_per_sec', 'value': value, 'unit': '10s-clips/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else args.precision,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
             'data': 'synthetic',
             'config': {'workload': f'BASELINE configs[1]: FBCRNN shallow (3.49M params) 128-mel, batch {B}/GPU of 10 s / '
                                    '16 kHz clips, K=10, fp32, full train step (GPU STFT+logmel, CNN, fwd+bwd GRU, '
@@ -327,7 +327,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'tf32x3', 'bf16'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -358,6 +358,10 @@ static int launch_wgrad(const TapParams& p, const float* in, const float* scale,
   return pbsed_after_launch();
 }
 
+int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                              const float* shift, const int* seq_len, const float* dout,
+                              int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled);
+
 extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                                    const float* shift, const int* seq_len, const float* dout,
                                    int mask_out, float* dW, float* dbias, void* stream) {
@@ -367,6 +371,11 @@ extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in,
   if (!in || !dout || !dW) return PBSED_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return PBSED_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision != 0) {
+    int handled = 0;
+    rc = tapgemm_wgrad_tc_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
+    if (handled || rc) return rc;
+  }
   if (p.Cout <= 16 && p.Cin <= 16)
     return launch_wgrad<16, 16, 2, 2, 32>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st);
   if (p.Cout <= 32 || p.Cin <= 32)

@@ -367,6 +367,283 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   }
 }
 
+
+// =====================================================================================
+// weight gradient on the tensor cores:
+//   dW[tap][n][c] += sum_rows dout[row][n] * a[row + off(tap)][c]
+// D[M = n][N = c] = A[n][K = rows] * B[c][K = rows]^T.  Both operands must be K-major for kind::tf32,
+// i.e. every 16-byte chunk holds 4 K-indices of one channel, so the producers transpose 4x4 blocks in
+// registers.  The sum over K is order-free, so a stage of 32 frames is chunked with STRIDE 8:
+//     chunk j = frames { t0+j, t0+j+8, t0+j+16, t0+j+24 },   j = 0..7 (dout)   j = -1..8 (input)
+// which turns the dt = -1/0/+1 time taps into WHOLE-CHUNK shifts: tap dt pairs dout chunk j with
+// input chunk j+dt, a +-LBO descriptor offset into one image (10 chunks instead of 3 shifted copies).
+// Operand rows are stored quad-major (row m = k*(C/4) + q for channel 4q+k) so the transposed float4
+// stores of a warp are contiguous; the epilogue undoes the permutation when it adds into dW.
+// One CTA owns (df group, <=128-wide n slice, <=128-wide c slice) and a strided subset of
+// (b, fo, 128-frame) work units; its <= 3 tap accumulators stay in TMEM for the whole kernel.
+constexpr int WG_KR = 32;                 // frames (K) per stage: four K=8 MMA steps
+constexpr int WG_ZCH = 8, WG_ACH = 10;    // chunks per stage image (dout / input incl. halo)
+constexpr int WG_STAGES = 2;
+constexpr int WG_TB = 128;                // frames per work unit
+
+struct WgParams {
+  int B, F_in, F_out, T, Cin, Cout;
+  int relu, per_f, mask_out;
+  int in_stride, out_stride;
+  long long w_tap_stride, w_sn, w_sc;
+  int Ms, Nc, m_slices, c_slices;
+  int ngroups;
+  int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
+  int row_splits;
+};
+
+struct __align__(16) WgCtl {
+  uint64_t full[WG_STAGES], empty[WG_STAGES], acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t o, float a, float b, float c, float d) {
+  float4 h;
+  h.x = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  h.y = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  h.z = __uint_as_float(__float_as_uint(c) & 0xFFFFE000u);
+  h.w = __uint_as_float(__float_as_uint(d) & 0xFFFFE000u);
+  *reinterpret_cast<float4*>(hi + o) = h;
+  *reinterpret_cast<float4*>(lo + o) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+}
+
+constexpr int WG_PROD = 256;              // producer threads (warps 0-7); warp 8 issues the MMAs
+
+__global__ void __launch_bounds__(WG_PROD + 32)
+wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restrict__ scale,
+                const float* __restrict__ shift, const int* __restrict__ seq_len,
+                const float* __restrict__ dout, float* __restrict__ dW, float* __restrict__ dbias) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int zq = p.Ms / 4, aq = p.Nc / 4;           // channel quads per operand
+  const uint32_t Z_LBO = 128 * 16, A_LBO = (uint32_t)p.Nc * 16;
+  const uint32_t Z_PART = WG_ZCH * Z_LBO, A_PART = WG_ACH * A_LBO;
+  const uint32_t STAGE = 2 * Z_PART + 2 * A_PART;
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem_raw + WG_STAGES * STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int c_slice = blockIdx.z % p.c_slices, m_slice = blockIdx.z / p.c_slices;
+  const int m0 = m_slice * p.Ms, c0 = c_slice * p.Nc;
+  const int df = p.g_df[g], ntap = p.g_n[g];
+  const int t_blocks = (p.T + WG_TB - 1) / WG_TB;
+  const int total_units = p.B * p.F_out * t_blocks;
+  const bool do_bias = dbias != nullptr && g == 0 && c_slice == 0;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ntap * p.Nc) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&ctl->full[i], WG_PROD); mbar_init(&ctl->empty[i], 1); }
+    mbar_init(&ctl->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_PROD / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (p.Ms < 128) {      // operand rows m >= Ms are read by the M = 128 MMA but never produced: zero once
+    for (int s = 0; s < WG_STAGES; ++s)
+      for (int part = 0; part < 2; ++part)
+        for (int ch = 0; ch < WG_ZCH; ++ch) {
+          float4* base = reinterpret_cast<float4*>(smem_raw + s * STAGE + part * Z_PART + ch * Z_LBO);
+          for (int i = p.Ms + tid; i < 128; i += WG_PROD + 32) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < WG_PROD / 32) {
+    // ============================== producers ==============================
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int zqi = tid % zq;                      // invariant: WG_PROD % zq == 0
+    const int aqi = tid % aq;
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+      const int tb = u % t_blocks, gq = u / t_blocks;
+      const int fo = gq % p.F_out, b = gq / p.F_out;
+      const int f_src = fo + df;
+      const bool f_ok = f_src >= 0 && f_src < p.F_in;
+      if (!f_ok && !do_bias) continue;
+      const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+      const int len_out = p.mask_out ? len_b : p.T;
+      const float* zsrc = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
+      const float* asrc = in + ((long long)b * p.F_in + f_src) * p.T * p.in_stride + c0 + aqi * 4;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (scale && f_ok) {
+        const int aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
+        sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
+        sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+      }
+      const int t_end = min(p.T, (tb + 1) * WG_TB);
+      for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR) {
+        if (!f_ok) {                                 // bias-only visit of a border row group
+          for (int j = tid / zq; j < WG_ZCH; j += WG_PROD / zq)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = t0 + j + 8 * i;
+              if (t < len_out) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+              }
+            }
+          continue;
+        }
+        const int slot = it % WG_STAGES;
+        mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);
+        uint8_t* z_hi = smem_raw + slot * STAGE;
+        uint8_t* z_lo = z_hi + Z_PART;
+        uint8_t* a_hi = z_lo + Z_PART;
+        uint8_t* a_lo = a_hi + A_PART;
+        // every thread first issues ALL its loads of this stage (<= 2 dout tasks + <= 3 input tasks of
+        // four 16-byte loads each), then transposes 4x4 blocks and stores quad-major K-major chunks
+        constexpr int ZT = 2, AT = 3;
+        float4 zv[ZT][4], av[AT][4];
+        const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
+#pragma unroll
+        for (int k = 0; k < ZT; ++k) {
+          const int j = zj0 + k * zjs;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int t = t0 + j + 8 * i;
+            zv[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < WG_ZCH && t < len_out)
+              zv[k][i] = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < AT; ++k) {
+          const int jj = aj0 + k * ajs;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int t = t0 + jj - 1 + 8 * i;
+            av[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jj < WG_ACH && t >= 0 && t < len_b)
+              av[k][i] = __ldg(reinterpret_cast<const float4*>(asrc + (long long)t * p.in_stride));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < ZT; ++k) {
+          const int j = zj0 + k * zjs;
+          if (j >= WG_ZCH) break;
+          const float4* v = zv[k];
+          const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
+          split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x);
+          split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y);
+          split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z);
+          split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w);
+          if (do_bias) {
+            bsum.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); bsum.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+            bsum.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); bsum.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < AT; ++k) {
+          const int jj = aj0 + k * ajs;
+          if (jj >= WG_ACH) break;
+          float4* v = av[k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int t = t0 + jj - 1 + 8 * i;
+            if (t >= 0 && t < len_b) {
+              float4 x = v[i];
+              if (scale) {
+                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+              }
+              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              v[i] = x;
+            }
+          }
+          const uint32_t o = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
+          split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x);
+          split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y);
+          split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z);
+          split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w);
+        }
+        fence_async_smem();
+        mbar_arrive(&ctl->full[slot]);
+        ++it;
+      }
+    }
+    if (do_bias) {
+      float* db = dbias + m0 + zqi * 4;
+      if (bsum.x != 0.f) atomicAdd(db + 0, bsum.x);
+      if (bsum.y != 0.f) atomicAdd(db + 1, bsum.y);
+      if (bsum.z != 0.f) atomicAdd(db + 2, bsum.z);
+      if (bsum.w != 0.f) atomicAdd(db + 3, bsum.w);
+    }
+    // ============================== epilogue ==============================
+    mbar_wait(&ctl->acc_full, 0);
+    tc_fence_after();
+    const int lw = warp & 3, half = warp >> 2;              // TMEM lane quarter / column half
+    const int m = lw * 32 + lane;                            // operand row -> channel (quad-major)
+    const int n = m0 + 4 * (m % zq) + m / zq;
+    if (it > 0) {                                            // no MMA issued -> TMEM is uninitialised
+      for (int j = 0; j < ntap; ++j) {
+        float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
+        for (int cc = half * 16; cc < p.Nc; cc += 32) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
+          if (m < p.Ms) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int ci = cc + k;
+              const int c = c0 + 4 * (ci % aq) + ci / aq;
+              if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TILE_M, p.Nc);
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out;
+        const int f_src = fo + df;
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR) {
+          const int slot = it % WG_STAGES;
+          mbar_wait(&ctl->full[slot], (it / WG_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t z_hi = smem_u32(smem_raw + slot * STAGE), z_lo = z_hi + Z_PART;
+          const uint32_t a_hi = z_lo + Z_PART, a_lo = a_hi + A_PART;
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
+            const int dt = p.g_dt[g][j];
+#pragma unroll
+            for (int ks = 0; ks < WG_KR / 8; ++ks) {
+              const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
+              const uint64_t dzh = make_desc(z_hi + zo, Z_LBO, 128), dzl = make_desc(z_lo + zo, Z_LBO, 128);
+              const uint64_t dah = make_desc(a_hi + ao, A_LBO, 128), dal = make_desc(a_lo + ao, A_LBO, 128);
+              mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+              mma_tf32(d, dzl, dah, idesc, 1u);
+              mma_tf32(d, dzh, dal, idesc, 1u);
+            }
+          }
+          mma_commit(&ctl->empty[slot]);
+          ++it;
+        }
+      }
+      mma_commit(&ctl->acc_full);
+    }
+  }
+  __syncthreads();
+  if (warp == WG_PROD / 32) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace
 
 // per-row-tile "first" flag: the first MMA into EACH accumulator must overwrite.  The loop above
@@ -441,6 +718,52 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
                                                   ep_scale, ep_shift, t_super);
   if (mt == 4) { PBSED_TC_LAUNCH(4) } else if (mt == 2) { PBSED_TC_LAUNCH(2) } else { PBSED_TC_LAUNCH(1) }
 #undef PBSED_TC_LAUNCH
+  *handled = 1;
+  return pbsed_after_launch();
+}
+
+int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                              const float* shift, const int* seq_len, const float* dout,
+                              int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (d->precision != 1 || !tc_eligible(d)) return 0;
+  if (d->Cin > NSLICE && d->Cin % NSLICE) return 0;
+  // measured crossover (B200, B=32): with <= 32 channels on a side the 128-lane MMA is mostly padding
+  // and the FFMA kernel wins; see DESIGN.md
+  if (!(d->Cin >= 64 || (d->Cin >= 32 && d->Cout >= 128))) return 0;
+  if ((((uintptr_t)in | (uintptr_t)dout | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return 0;
+  WgParams p = {};
+  p.B = d->B; p.F_in = d->F_in; p.F_out = d->F_out; p.T = d->T; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.relu = d->relu; p.per_f = d->per_f; p.mask_out = mask_out;
+  p.in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
+  p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+  p.w_tap_stride = d->w_tap_stride; p.w_sn = d->w_sn; p.w_sc = d->w_sc;
+  p.Ms = d->Cout < NSLICE ? d->Cout : NSLICE;
+  p.m_slices = d->Cout / p.Ms;
+  p.Nc = d->Cin < NSLICE ? d->Cin : NSLICE;
+  p.c_slices = d->Cin / p.Nc;
+  if (WG_PROD % (p.Ms / 4) || WG_PROD % (p.Nc / 4)) return 0;     // producer thread mapping
+  if (2 * (WG_PROD / (p.Ms / 4)) < WG_ZCH || 3 * (WG_PROD / (p.Nc / 4)) < WG_ACH) return 0;
+  for (int i = 0; i < d->ntaps; ++i) {
+    int g = 0;
+    for (; g < p.ngroups; ++g)
+      if (p.g_df[g] == d->df[i] && p.g_n[g] < 3) break;
+    if (g == p.ngroups) { p.g_df[g] = d->df[i]; p.g_n[g] = 0; ++p.ngroups; }
+    p.g_tap[g][p.g_n[g]] = i; p.g_dt[g][p.g_n[g]] = d->dt[i]; ++p.g_n[g];
+  }
+  const int roles = p.ngroups * p.m_slices * p.c_slices;
+  const int units = p.B * p.F_out * cdiv(p.T, WG_TB);
+  int rs = (2 * 148) / roles;                       // <= 2 CTAs per SM's worth, never a ragged extra wave
+  if (rs >= 8 * 2 && units / rs < 4) rs = 148 / roles;
+  if (rs > units) rs = units;
+  if (rs < 1) rs = 1;
+  p.row_splits = rs;
+  const size_t stage = 2 * (size_t)WG_ZCH * 128 * 16 + 2 * (size_t)WG_ACH * p.Nc * 16;
+  const size_t smem = WG_STAGES * stage + sizeof(WgCtl) + 128;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(rs, p.ngroups, p.m_slices * p.c_slices);
+  wgrad_tc_kernel<<<grid, WG_PROD + 32, smem, st>>>(p, in, scale, shift, seq_len, dout, dW, dbias);
   *handled = 1;
   return pbsed_after_launch();
 }

@@ -20,7 +20,7 @@ from ._lib import TapGemmDesc, call
 import os
 
 PRECISION = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
-_default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'fp32')]
+_default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'tf32x3')]
 
 
 def set_default_precision(p):

@@ -84,3 +84,66 @@ def test_tc_dgrad_with_relu_mask_epilogue(built_lib):
     out = run(1, dz, W, None, dims, rtaps, seq=seq, transpose_w=True, ep=(xprev, scale, shift))
     assert reldiff(out, ref) < 2e-5
     assert float((out == 0).float().mean()) > .3      # the ReLU mask really zeroed entries
+
+
+@pytest.mark.parametrize('B,F,T,Cin,Cout,taps,relu', [
+    (2, 3, 37, 16, 16, TAPS_3x3, True),
+    (2, 4, 500, 32, 64, TAPS_3x3, True),
+    (2, 2, 300, 128, 256, TAPS_3x3, True),
+    (3, 1, 500, 256, 768, TAPS_1x1, False),
+    (2, 1, 300, 256, 256, TAPS_1x3, True),
+    (2, 1, 200, 256, 128, [(0, -1)], False),
+])
+def test_tc_wgrad_matches_ffma(built_lib, B, F, T, Cin, Cout, taps, relu):
+    from pb_sed_b200 import ops
+    torch.manual_seed(Cin + Cout + T)
+    x = torch.randn(B, F, T, Cin, device=DEV)
+    dz = torch.randn(B, F, T, Cout, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    sl = np.minimum(np.array([T, max(T - 3, 1), max(T // 2, 1)][:B]), T)
+    seq = ops.SeqLen.make(sl, B, T, DEV)
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, F, F, T, Cin, Cout, taps, relu=relu, precision=prec)
+        dW = torch.zeros(len(taps), Cout, Cin, device=DEV)
+        db = torch.zeros(Cout, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, db, scale if relu else None, shift if relu else None, seq, mask_out=True)
+        res.append((dW, db))
+    assert reldiff(res[1][0], res[0][0]) < 5e-5
+    assert reldiff(res[1][1], res[0][1]) < 5e-5
+    assert float(res[0][0].abs().max()) > 0
+
+
+def test_tc_wgrad_flatten_and_strided_input(built_lib):
+    """per-(f,c) affine with 8 frequency taps; and the GRU W_hh gradient reading one direction's half of a
+    (B,T,2H) map (in_stride = 2H)."""
+    from pb_sed_b200 import ops
+    import ctypes
+    torch.manual_seed(3)
+    B, Fh, T, Cin, Cout = 2, 8, 200, 64, 128
+    taps = [(f, 0) for f in range(Fh)]
+    x = torch.randn(B, Fh, T, Cin, device=DEV)
+    dz = torch.randn(B, 1, T, Cout, device=DEV)
+    scale = torch.rand(Fh * Cin, device=DEV) + .5
+    shift = torch.randn(Fh * Cin, device=DEV) * .3
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, Fh, 1, T, Cin, Cout, taps, relu=True, per_f=True, precision=prec)
+        dW = torch.zeros(len(taps), Cout, Cin, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, None, scale, shift, None, mask_out=False)
+        res.append(dW)
+    assert reldiff(res[1], res[0]) < 5e-5
+    H = 64
+    h = torch.randn(B, T, 2 * H, device=DEV)
+    dgh = torch.randn(B, T, 3 * H, device=DEV)
+    seq = ops.SeqLen.make(np.array([T, T - 50]), B, T, DEV)
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, 1, 1, T, H, 3 * H, [(0, 1)], in_stride=2 * H, precision=prec)
+        dW = torch.zeros(1, 3 * H, H, device=DEV)
+        db = torch.zeros(3 * H, device=DEV)
+        ops.tapgemm_wgrad(None, dgh, desc, dW, db, None, None, seq, mask_out=True,
+                          x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * H))
+        res.append((dW, db))
+    assert reldiff(res[1][0], res[0][0]) < 5e-5 and reldiff(res[1][1], res[0][1]) < 5e-5
