@@ -1,0 +1,148 @@
+// conv_cin1.cu -- the first CNN2d layer: ONE input channel (the log-mel map), <= 32 output channels.
+//
+// Reference: layer 0 of padertorch CNN2d as configured at
+// pb_sed/experiments/weak_label_crnn/training.py:218-230 (input_layer: no norm / activation; 3x3,
+// 1 -> 16 channels).  K = 9 MACs per output: a GEMM tile would be all padding, the layer is pure
+// HBM streaming (read 1 float, write Cout floats per frame), so it gets a direct kernel:
+// one thread per output frame, weights in shared memory, 64-byte contiguous stores per thread.
+#include "common.cuh"
+
+struct Cin1Params {
+  int B, F_in, F_out, T, Cout, ntaps;
+  int df[PBSED_MAX_TAPS], dt[PBSED_MAX_TAPS];
+  int relu;
+  int out_stride;
+};
+
+__device__ __forceinline__ float cin1_load(const float* __restrict__ in, const Cin1Params& p, int b, int f,
+                                           int t, int len_b, float sc, float sh, bool affine) {
+  if (f < 0 || f >= p.F_in || t < 0 || t >= len_b) return 0.f;
+  float v = __ldg(in + ((long long)b * p.F_in + f) * p.T + t);
+  if (affine) v = fmaf(v, sc, sh);
+  if (p.relu) v = fmaxf(v, 0.f);
+  return v;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_cin1_fwd_kernel(Cin1Params p, const float* __restrict__ in, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const int* __restrict__ seq_len,
+                     const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ out) {
+  __shared__ float ws[PBSED_MAX_TAPS][COUT];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < p.ntaps * COUT; i += 256) ws[i / COUT][i % COUT] = __ldg(W + i);   // (tap, n, c=0)
+  for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = bias ? __ldg(bias + i) : 0.f;
+  __syncthreads();
+  const int fo = blockIdx.y, b = blockIdx.z;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= p.T) return;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+  const bool affine = scale != nullptr;
+  const float sc = affine ? __ldg(scale) : 1.f, sh = affine ? __ldg(shift) : 0.f;
+  float acc[COUT];
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) acc[n] = bs[n];
+  for (int tap = 0; tap < p.ntaps; ++tap) {
+    const float a = cin1_load(in, p, b, fo + p.df[tap], t + p.dt[tap], len_b, sc, sh, affine);
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) acc[n] = fmaf(a, ws[tap][n], acc[n]);
+  }
+  float* dst = out + (((long long)b * p.F_out + fo) * p.T + t) * p.out_stride;
+#pragma unroll
+  for (int n = 0; n < COUT; n += 4)
+    *reinterpret_cast<float4*>(dst + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+}
+
+// dW[tap][n] += sum_rows dout[row][n] * a[row + off(tap)];  dbias[n] += sum_rows dout[row][n]
+// thread = (row lane, channel n); 256 / COUT row lanes stride over the CTA's frames.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const int* __restrict__ seq_len,
+                       const float* __restrict__ dout, int mask_out, float* __restrict__ dW,
+                       float* __restrict__ dbias, int groups_per_cta) {
+  constexpr int RL = 256 / COUT;
+  __shared__ float red[PBSED_MAX_TAPS + 1][256];
+  const int n = threadIdx.x % COUT, rl = threadIdx.x / COUT;
+  const bool affine = scale != nullptr;
+  const float sc = affine ? __ldg(scale) : 1.f, sh = affine ? __ldg(shift) : 0.f;
+  float acc[PBSED_MAX_TAPS];
+#pragma unroll
+  for (int i = 0; i < PBSED_MAX_TAPS; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  const int total = p.B * p.F_out;
+  const int g0 = blockIdx.x * groups_per_cta, g1 = min(g0 + groups_per_cta, total);
+  for (int g = g0; g < g1; ++g) {
+    const int b = g / p.F_out, fo = g % p.F_out;
+    const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+    const int len_out = mask_out ? len_b : p.T;
+    const float* z = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + n;
+    for (int t = rl; t < len_out; t += RL) {
+      const float dz = __ldg(z + (long long)t * p.out_stride);
+      bsum += dz;
+#pragma unroll
+      for (int tap = 0; tap < PBSED_MAX_TAPS; ++tap) {
+        if (tap < p.ntaps)
+          acc[tap] = fmaf(dz, cin1_load(in, p, b, fo + p.df[tap], t + p.dt[tap], len_b, sc, sh, affine), acc[tap]);
+      }
+    }
+  }
+  for (int tap = 0; tap < p.ntaps; ++tap) red[tap][threadIdx.x] = acc[tap];
+  red[PBSED_MAX_TAPS][threadIdx.x] = bsum;
+  __syncthreads();
+  for (int i = threadIdx.x; i < (p.ntaps + 1) * COUT; i += 256) {
+    const int tap = i / COUT, nn = i % COUT;
+    const int row = tap < p.ntaps ? tap : PBSED_MAX_TAPS;
+    float s = 0.f;
+    for (int r = 0; r < RL; ++r) s += red[row][r * COUT + nn];
+    if (tap < p.ntaps) { if (s != 0.f) atomicAdd(dW + tap * COUT + nn, s); }
+    else if (dbias && s != 0.f) atomicAdd(dbias + nn, s);
+  }
+}
+
+static bool cin1_ok(const pbsed_tapgemm_desc* d) {
+  const int in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
+  const int out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+  return d->Cin == 1 && in_stride == 1 && (d->Cout == 16 || d->Cout == 32) && out_stride % 4 == 0 &&
+         d->w_sn == 1 && d->w_sc == 1 && d->w_tap_stride == d->Cout && d->per_f == 0 &&
+         d->F_out <= 65535 && d->B <= 65535;
+}
+
+static void cin1_fill(const pbsed_tapgemm_desc* d, Cin1Params& p) {
+  p.B = d->B; p.F_in = d->F_in; p.F_out = d->F_out; p.T = d->T; p.Cout = d->Cout; p.ntaps = d->ntaps;
+  for (int i = 0; i < d->ntaps; ++i) { p.df[i] = d->df[i]; p.dt[i] = d->dt[i]; }
+  p.relu = d->relu;
+  p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+}
+
+int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                           const float* shift, const int* seq_len, const float* W, const float* bias,
+                           float* out, const float* ep_src, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (!cin1_ok(d) || ep_src || (((uintptr_t)out) & 15)) return 0;
+  Cin1Params p;
+  cin1_fill(d, p);
+  dim3 grid(cdiv(p.T, 256), p.F_out, p.B);
+  if (p.Cout == 16) conv_cin1_fwd_kernel<16><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, W, bias, out);
+  else              conv_cin1_fwd_kernel<32><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, W, bias, out);
+  *handled = 1;
+  return pbsed_after_launch();
+}
+
+int conv_cin1_wgrad_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                             const float* shift, const int* seq_len, const float* dout, int mask_out,
+                             float* dW, float* dbias, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (!cin1_ok(d)) return 0;
+  Cin1Params p;
+  cin1_fill(d, p);
+  const int total = p.B * p.F_out;
+  int gpc = cdiv(total, 148 * 8);
+  if (gpc < 1) gpc = 1;
+  dim3 grid(cdiv(total, gpc));
+  if (p.Cout == 16) conv_cin1_wgrad_kernel<16><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc);
+  else              conv_cin1_wgrad_kernel<32><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc);
+  *handled = 1;
+  return pbsed_after_launch();
+}

@@ -18,6 +18,7 @@
 // the cluster through distributed shared memory, followed by one cluster barrier.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 namespace cg = cooperative_groups;
 
 struct GruDirs {             // per-direction operands: directions may belong to different modules
@@ -34,20 +35,56 @@ struct GruDirs {             // per-direction operands: directions may belong to
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <int H>
+// ---- cluster exchange without a cluster-scope fence in the time loop ------------------------
+// The per-step state (h, or the gate gradients) is pushed into every CTA of the cluster with
+// st.async: a remote shared-memory store that completes bytes on the DESTINATION CTA's mbarrier.
+// Consumers wait on their local mbarrier, so the loop needs no barrier.cluster / release fence --
+// which would also have to drain the step's global stores (h_out, saved gates): ncu showed that
+// membar stall as the top stall of the first version (profiles/r01_gru_ncu.txt).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void xbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void xbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "XW_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra XD_%=;\n"
+      "bra XW_%=;\n"
+      "XD_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+template <int H, int BC>
 __global__ void __launch_bounds__(256, 1)
 gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int h_stride) {
-  constexpr int NC = H / 32, KS = H / 8, BC = 8;
+  constexpr int NC = H / 32, KS = H / 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, q = tid >> 5, j = tid & 31;
   const int u = rank * 32 + j;
   const int d = blockIdx.z;
   const bool reverse = dirs.reverse[d] != 0;
-  const int bq = blockIdx.y * BC + q;
+  const bool ew = q < BC;                       // warps 0..BC-1 run the gate math for clip q
+  const int bq = ew ? blockIdx.y * BC + q : B;
 
   __shared__ __align__(16) float hbuf[2][BC][H];
   __shared__ float red[8][3][BC][32];
+  __shared__ __align__(8) uint64_t hbar[2];            // "buffer i holds the complete h of a step"
 
   const float* w = dirs.w_hh[d];
   const float* bh = dirs.b_hh[d];
@@ -59,21 +96,35 @@ gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
   const float bhr = __ldg(bh + u), bhz = __ldg(bh + H + u), bhn = __ldg(bh + 2 * H + u);
 
   for (int i = tid; i < 2 * BC * H; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+  if (tid == 0) {
+    xbar_init(&hbar[0], 1); xbar_init(&hbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
   const float* gi_b = dirs.gi[d] + (long long)bq * T * 3 * H;
   float* ho_b = dirs.h_out[d] + (long long)bq * T * h_stride;
   float* sv_b = dirs.save[d] ? dirs.save[d] + (long long)bq * T * 4 * H : nullptr;
   float hprev = 0.f;
+  // the input projections of step s+1 are fetched while step s computes (they are the only global
+  // loads on the recurrence's critical path)
+  float nxt_r = 0.f, nxt_z = 0.f, nxt_n = 0.f;
+  if (0 < len) {
+    const float* p = gi_b + (long long)(reverse ? len - 1 : 0) * 3 * H + u;
+    nxt_r = __ldg(p); nxt_z = __ldg(p + H); nxt_n = __ldg(p + 2 * H);
+  }
   cluster.sync();
 
   for (int s = 0; s < T; ++s) {
     const int cur = s & 1;
     const bool active = s < len;
     const int t = reverse ? (len - 1 - s) : s;
-    float gir = 0.f, giz = 0.f, gin = 0.f;
-    if (active) {
-      const float* p = gi_b + (long long)t * 3 * H + u;
-      gir = __ldg(p); giz = __ldg(p + H); gin = __ldg(p + 2 * H);
+    const float gir = nxt_r, giz = nxt_z, gin = nxt_n;
+    // arm the barrier of the buffer this step fills, then wait for the buffer this step reads
+    if (tid == 0) xbar_expect(&hbar[cur ^ 1], (uint32_t)(NC * BC * 32 * sizeof(float)));
+    if (s > 0) xbar_wait(&hbar[cur], (uint32_t)(((s - 1) >> 1) & 1));
+    if (s + 1 < len) {
+      const float* p = gi_b + (long long)(reverse ? len - 2 - s : s + 1) * 3 * H + u;
+      nxt_r = __ldg(p); nxt_z = __ldg(p + H); nxt_n = __ldg(p + 2 * H);
     }
     float acc[3][BC];
 #pragma unroll
@@ -100,9 +151,11 @@ gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
       for (int b = 0; b < BC; ++b) red[q][g][b][j] = acc[g][b];
     __syncthreads();
     float ghr = bhr, ghz = bhz, ghn = bhn;
+    if (ew) {
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) {
-      ghr += red[qq][0][q][j]; ghz += red[qq][1][q][j]; ghn += red[qq][2][q][j];
+      for (int qq = 0; qq < 8; ++qq) {
+        ghr += red[qq][0][q][j]; ghz += red[qq][1][q][j]; ghn += red[qq][2][q][j];
+      }
     }
     float hnew = hprev;
     if (active) {
@@ -119,29 +172,36 @@ gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
       ho_b[(long long)s * h_stride + u] = 0.f;       // padded frame t = s >= len
     }
     hprev = hnew;
-    float* mine = &hbuf[cur ^ 1][q][u];
+    if (ew) {
+      const uint32_t mine = smem_addr(&hbuf[cur ^ 1][q][u]), bar = smem_addr(&hbar[cur ^ 1]);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) *cluster.map_shared_rank(mine, c) = hnew;
-    cluster.sync();
+      for (int c = 0; c < NC; ++c) st_async_f32(mapa_rank(mine, c), hnew, mapa_rank(bar, c));
+    }
+    // red[] is rewritten by the next step's matvec only after every warp passed this step's reads:
+    // the wait above (all threads) sits between them, but a CTA-local barrier keeps it explicit
+    __syncthreads();
   }
+  cluster.sync();      // no CTA may exit while peers can still push into its shared memory
 }
 
 // ------------------------------------------------------------------ BPTT
-template <int H>
+template <int H, int BC>
 __global__ void __launch_bounds__(256, 1)
 gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int h_stride) {
-  constexpr int NC = H / 32, KS = H / 8, BC = 8;
+  constexpr int NC = H / 32, KS = H / 8;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, q = tid >> 5, j = tid & 31;
   const int u = rank * 32 + j;
   const int d = blockIdx.z;
   const bool reverse = dirs.reverse[d] != 0;
-  const int bq = blockIdx.y * BC + q;
+  const bool ew = q < BC;
+  const int bq = ew ? blockIdx.y * BC + q : B;
 
   extern __shared__ __align__(16) float smem[];
   float* dg = smem;                            // [2][3][BC][H]
   float* red = smem + 2 * 3 * BC * H;          // [8][BC][32]
+  __shared__ __align__(8) uint64_t gbar[2];
 
   const float* w = dirs.w_hh[d];
   float Wt[3][KS];
@@ -157,19 +217,35 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
   float* dgi_b = dirs.dgi[d] + (long long)bq * T * 3 * H;
   float* dgh_b = dirs.dgh[d] + (long long)bq * T * 3 * H;
   float dh_carry = 0.f;
+  // operands of the NEXT processed step (s-1) are fetched while step s computes
+  float n_dho = 0.f, n_r = 0.f, n_z = 0.f, n_n = 0.f, n_ghn = 0.f, n_hp = 0.f;
+  auto fetch = [&](int s) {
+    if (s >= 0 && s < len) {
+      const int t = reverse ? (len - 1 - s) : s;
+      n_dho = __ldg(dho_b + (long long)t * h_stride + u);
+      const float* sp = sv_b + (long long)t * 4 * H + u;
+      n_r = __ldg(sp); n_z = __ldg(sp + H); n_n = __ldg(sp + 2 * H); n_ghn = __ldg(sp + 3 * H);
+      n_hp = s > 0 ? __ldg(ho_b + (long long)(reverse ? t + 1 : t - 1) * h_stride + u) : 0.f;
+    }
+  };
+  fetch(T - 1);
+  if (tid == 0) {
+    xbar_init(&gbar[0], 1); xbar_init(&gbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cluster.sync();
+  int fills0 = 0, fills1 = 0;                  // completed fills per buffer -> wait parity
 
   for (int s = T - 1; s >= 0; --s) {
     const int cur = s & 1;
     const bool active = s < len;
     const int t = reverse ? (len - 1 - s) : s;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f, direct = dh_carry;
+    if (tid == 0) xbar_expect(&gbar[cur], (uint32_t)(3 * NC * BC * 32 * sizeof(float)));
+    const float c_dho = n_dho, r = n_r, z = n_z, n = n_n, ghn = n_ghn, hp = n_hp;
+    fetch(s - 1);
     if (active) {
-      const float dh = dh_carry + __ldg(dho_b + (long long)t * h_stride + u);
-      const float* sp = sv_b + (long long)t * 4 * H + u;
-      const float r = __ldg(sp), z = __ldg(sp + H), n = __ldg(sp + 2 * H), ghn = __ldg(sp + 3 * H);
-      float hp = 0.f;
-      if (s > 0) hp = __ldg(ho_b + (long long)(reverse ? t + 1 : t - 1) * h_stride + u);
+      const float dh = dh_carry + c_dho;
       const float dn = dh * (1.f - z) * (1.f - n * n);
       const float dz = dh * (hp - n) * z * (1.f - z);
       const float dr = dn * ghn * r * (1.f - r);
@@ -185,16 +261,24 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
       float* hp2 = dgh_b + (long long)s * 3 * H + u;
       hp2[0] = 0.f; hp2[H] = 0.f; hp2[2 * H] = 0.f;
     }
-    float* m0 = dg + ((cur * 3 + 0) * BC + q) * H + u;
-    float* m1 = dg + ((cur * 3 + 1) * BC + q) * H + u;
-    float* m2 = dg + ((cur * 3 + 2) * BC + q) * H + u;
+    if (ew) {
+      const uint32_t m0 = smem_addr(dg + ((cur * 3 + 0) * BC + q) * H + u);
+      const uint32_t m1 = smem_addr(dg + ((cur * 3 + 1) * BC + q) * H + u);
+      const uint32_t m2 = smem_addr(dg + ((cur * 3 + 2) * BC + q) * H + u);
+      const uint32_t bar = smem_addr(&gbar[cur]);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      *cluster.map_shared_rank(m0, c) = v0;
-      *cluster.map_shared_rank(m1, c) = v1;
-      *cluster.map_shared_rank(m2, c) = v2;
+      for (int c = 0; c < NC; ++c) {
+        const uint32_t rb = mapa_rank(bar, c);
+        st_async_f32(mapa_rank(m0, c), v0, rb);
+        st_async_f32(mapa_rank(m1, c), v1, rb);
+        st_async_f32(mapa_rank(m2, c), v2, rb);
+      }
     }
-    cluster.sync();
+    {
+      int& fills = cur ? fills1 : fills0;
+      xbar_wait(&gbar[cur], (uint32_t)(fills & 1));
+      ++fills;
+    }
     float acc[BC];
 #pragma unroll
     for (int b = 0; b < BC; ++b) acc[b] = 0.f;
@@ -214,25 +298,29 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
     for (int b = 0; b < BC; ++b) red[(q * BC + b) * 32 + j] = acc[b];
     __syncthreads();
     float sum = direct;
+    if (ew) {
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) sum += red[(qq * BC + q) * 32 + j];
+      for (int qq = 0; qq < 8; ++qq) sum += red[(qq * BC + q) * 32 + j];
+    }
     dh_carry = sum;
+    __syncthreads();     // red[] is free for the next step
   }
+  cluster.sync();        // no CTA may exit while peers can still push into its shared memory
 }
 
 // ------------------------------------------------------------------ launchers
-template <int H, bool BWD>
-static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs& dirs, int h_stride,
-                      cudaStream_t st) {
+template <int H, bool BWD, int BC>
+static int launch_gru_bc(const int* seq_len, int B, int T, int ndir, const GruDirs& dirs, int h_stride,
+                         cudaStream_t st) {
   size_t smem = 0;
   cudaError_t e;
   if (BWD) {
-    smem = (size_t)(2 * 3 * 8 * H + 8 * 8 * 32) * sizeof(float);
-    e = cudaFuncSetAttribute(gru_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem = (size_t)(2 * 3 * BC * H + 8 * BC * 32) * sizeof(float);
+    e = cudaFuncSetAttribute(gru_bwd_kernel<H, BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(H / 32, cdiv(B, 8), ndir);
+  cfg.gridDim = dim3(H / 32, cdiv(B, BC), ndir);
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -240,12 +328,23 @@ static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs&
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (BWD) e = cudaLaunchKernelEx(&cfg, gru_bwd_kernel<H>, seq_len, B, T, dirs, h_stride);
-  else     e = cudaLaunchKernelEx(&cfg, gru_fwd_kernel<H>, seq_len, B, T, dirs, h_stride);
+  if (BWD) e = cudaLaunchKernelEx(&cfg, gru_bwd_kernel<H, BC>, seq_len, B, T, dirs, h_stride);
+  else     e = cudaLaunchKernelEx(&cfg, gru_fwd_kernel<H, BC>, seq_len, B, T, dirs, h_stride);
   ++g_pbsed_launches;
   if (e != cudaSuccess) return (int)e;
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+// clips per cluster: 8 (measured faster than 4 at B = 32 even though 4 halves the FMAs per step;
+// PBSED_GRU_BC=4 forces the other variant for experiments)
+template <int H, bool BWD>
+static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs& dirs, int h_stride,
+                      cudaStream_t st) {
+  static const int force_bc = getenv("PBSED_GRU_BC") ? atoi(getenv("PBSED_GRU_BC")) : 0;
+  if (force_bc == 4)
+    return launch_gru_bc<H, BWD, 4>(seq_len, B, T, ndir, dirs, h_stride, st);
+  return launch_gru_bc<H, BWD, 8>(seq_len, B, T, ndir, dirs, h_stride, st);
 }
 
 template <bool BWD>

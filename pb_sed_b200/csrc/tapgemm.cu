@@ -214,6 +214,13 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
                         const float* ep_shift, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled);
 
+int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                           const float* shift, const int* seq_len, const float* W, const float* bias,
+                           float* out, const float* ep_src, cudaStream_t st, int* handled);
+int conv_cin1_wgrad_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                             const float* shift, const int* seq_len, const float* dout, int mask_out,
+                             float* dW, float* dbias, cudaStream_t st, int* handled);
+
 extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                              const float* shift, const int* seq_len, const float* W,
                              const float* bias, float* out, const float* ep_src,
@@ -225,6 +232,11 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   if (!in || !W || !out) return PBSED_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return PBSED_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    int handled = 0;
+    rc = conv_cin1_fwd_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, st, &handled);
+    if (handled || rc) return rc;
+  }
   if (d->precision != 0) {
     int handled = 0;
     rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
@@ -371,6 +383,11 @@ extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in,
   if (!in || !dout || !dW) return PBSED_EINVAL;
   if ((scale == nullptr) != (shift == nullptr)) return PBSED_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    int handled = 0;
+    rc = conv_cin1_wgrad_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
+    if (handled || rc) return rc;
+  }
   if (d->precision != 0) {
     int handled = 0;
     rc = tapgemm_wgrad_tc_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
