@@ -35,6 +35,17 @@ struct GruDirs {             // per-direction operands: directions may belong to
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// packed 2 x fp32 FMA (Blackwell FFMA2): halves the instruction count of the recurrent mat-vec,
+// which ncu showed to be issue-bound (57 % issue-active, 6144 of 8580 warp instructions per step)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // ---- cluster exchange without a cluster-scope fence in the time loop ------------------------
 // The per-step state (h, or the gate gradients) is pushed into every CTA of the cluster with
 // st.async: a remote shared-memory store that completes bytes on the DESTINATION CTA's mbarrier.
@@ -88,11 +99,13 @@ gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
 
   const float* w = dirs.w_hh[d];
   const float* bh = dirs.b_hh[d];
-  float W[3][KS];
+  float2 W[3][KS / 2];                         // (k, k+1) pairs: FFMA2 accumulates even / odd k separately
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) W[g][kk] = __ldg(w + (long long)(g * H + u) * H + q * KS + kk);
+    for (int kk = 0; kk < KS / 2; ++kk)
+      W[g][kk] = make_float2(__ldg(w + (long long)(g * H + u) * H + q * KS + 2 * kk),
+                             __ldg(w + (long long)(g * H + u) * H + q * KS + 2 * kk + 1));
   const float bhr = __ldg(bh + u), bhz = __ldg(bh + H + u), bhn = __ldg(bh + 2 * H + u);
 
   for (int i = tid; i < 2 * BC * H; i += 256) (&hbuf[0][0][0])[i] = 0.f;
@@ -126,29 +139,28 @@ gru_fwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
       const float* p = gi_b + (long long)(reverse ? len - 2 - s : s + 1) * 3 * H + u;
       nxt_r = __ldg(p); nxt_z = __ldg(p + H); nxt_n = __ldg(p + 2 * H);
     }
-    float acc[3][BC];
+    float2 acc[3][BC];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int b = 0; b < BC; ++b) acc[g][b] = 0.f;
+      for (int b = 0; b < BC; ++b) acc[g][b] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int kk = 0; kk < KS; kk += 4) {
 #pragma unroll
       for (int b = 0; b < BC; ++b) {
         const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][b][q * KS + kk]);
+        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-          acc[g][b] = fmaf(W[g][kk], hv.x, acc[g][b]);
-          acc[g][b] = fmaf(W[g][kk + 1], hv.y, acc[g][b]);
-          acc[g][b] = fmaf(W[g][kk + 2], hv.z, acc[g][b]);
-          acc[g][b] = fmaf(W[g][kk + 3], hv.w, acc[g][b]);
+          acc[g][b] = ffma2(W[g][kk / 2], h01, acc[g][b]);
+          acc[g][b] = ffma2(W[g][kk / 2 + 1], h23, acc[g][b]);
         }
       }
     }
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int b = 0; b < BC; ++b) red[q][g][b][j] = acc[g][b];
+      for (int b = 0; b < BC; ++b) red[q][g][b][j] = acc[g][b].x + acc[g][b].y;
     __syncthreads();
     float ghr = bhr, ghz = bhz, ghn = bhn;
     if (ew) {
@@ -204,11 +216,13 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
   __shared__ __align__(8) uint64_t gbar[2];
 
   const float* w = dirs.w_hh[d];
-  float Wt[3][KS];
+  float2 Wt[3][KS / 2];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) Wt[g][kk] = __ldg(w + (long long)(g * H + q * KS + kk) * H + u);
+    for (int kk = 0; kk < KS / 2; ++kk)
+      Wt[g][kk] = make_float2(__ldg(w + (long long)(g * H + q * KS + 2 * kk) * H + u),
+                              __ldg(w + (long long)(g * H + q * KS + 2 * kk + 1) * H + u));
 
   const int len = (bq < B) ? (seq_len ? min(__ldg(seq_len + bq), T) : T) : 0;
   const float* dho_b = dirs.dh_out[d] + (long long)bq * T * h_stride;
@@ -279,9 +293,9 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
       xbar_wait(&gbar[cur], (uint32_t)(fills & 1));
       ++fills;
     }
-    float acc[BC];
+    float2 acc[BC];
 #pragma unroll
-    for (int b = 0; b < BC; ++b) acc[b] = 0.f;
+    for (int b = 0; b < BC; ++b) acc[b] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
@@ -289,13 +303,11 @@ gru_bwd_kernel(const int* __restrict__ seq_len, int B, int T, GruDirs dirs, int 
 #pragma unroll
         for (int b = 0; b < BC; ++b) {
           const float4 dv = *reinterpret_cast<const float4*>(dg + ((cur * 3 + g) * BC + b) * H + q * KS + kk);
-          acc[b] = fmaf(Wt[g][kk], dv.x, acc[b]);
-          acc[b] = fmaf(Wt[g][kk + 1], dv.y, acc[b]);
-          acc[b] = fmaf(Wt[g][kk + 2], dv.z, acc[b]);
-          acc[b] = fmaf(Wt[g][kk + 3], dv.w, acc[b]);
+          acc[b] = ffma2(Wt[g][kk / 2], make_float2(dv.x, dv.y), acc[b]);
+          acc[b] = ffma2(Wt[g][kk / 2 + 1], make_float2(dv.z, dv.w), acc[b]);
         }
 #pragma unroll
-    for (int b = 0; b < BC; ++b) red[(q * BC + b) * 32 + j] = acc[b];
+    for (int b = 0; b < BC; ++b) red[(q * BC + b) * 32 + j] = acc[b].x + acc[b].y;
     __syncthreads();
     float sum = direct;
     if (ew) {
@@ -342,9 +354,21 @@ template <int H, bool BWD>
 static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs& dirs, int h_stride,
                       cudaStream_t st) {
   static const int force_bc = getenv("PBSED_GRU_BC") ? atoi(getenv("PBSED_GRU_BC")) : 0;
-  if (force_bc == 4)
-    return launch_gru_bc<H, BWD, 4>(seq_len, B, T, ndir, dirs, h_stride, st);
-  return launch_gru_bc<H, BWD, 8>(seq_len, B, T, ndir, dirs, h_stride, st);
+  int bc = force_bc;
+  if (bc == 0) {
+    // fewest clips per cluster whose clusters are all co-resident: an 8-CTA cluster needs 8 free SMs of
+    // one GPC and ~14 of them fit a B200 at once (16 clusters of the 4-clip variant at B = 32 ran in two
+    // rounds = 2x the time); fewer clips = fewer FMAs on the 500-step critical path
+    const int max_clusters = (H / 32 == 8) ? 14 : 148 / (H / 32);
+    bc = 8;
+    for (int c : {4, 5, 6}) if (cdiv(B, c) * ndir <= max_clusters) { bc = c; break; }
+  }
+  switch (bc) {
+    case 4: return launch_gru_bc<H, BWD, 4>(seq_len, B, T, ndir, dirs, h_stride, st);
+    case 5: return launch_gru_bc<H, BWD, 5>(seq_len, B, T, ndir, dirs, h_stride, st);
+    case 6: return launch_gru_bc<H, BWD, 6>(seq_len, B, T, ndir, dirs, h_stride, st);
+    default: return launch_gru_bc<H, BWD, 8>(seq_len, B, T, ndir, dirs, h_stride, st);
+  }
 }
 
 template <bool BWD>
