@@ -55,18 +55,22 @@ conv_cin1_fwd_kernel(Cin1Params p, const float* __restrict__ in, const float* __
 }
 
 // dW[tap][n] += sum_rows dout[row][n] * a[row + off(tap)];  dbias[n] += sum_rows dout[row][n]
-// thread = (row lane, channel n); 256 / COUT row lanes stride over the CTA's frames.
+// CTA = one (b, fo) row group at a time: the <= 3 source rows it touches are staged (transformed) in
+// shared memory once, then thread (frame lane, channel n) streams dout and reads the taps from smem.
+constexpr int CIN1_TMAX = 2048;
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* __restrict__ scale,
                        const float* __restrict__ shift, const int* __restrict__ seq_len,
                        const float* __restrict__ dout, int mask_out, float* __restrict__ dW,
-                       float* __restrict__ dbias, int groups_per_cta) {
+                       float* __restrict__ dbias, int groups_per_cta, int df_min, int n_rows, int dt_min, int halo) {
   constexpr int RL = 256 / COUT;
+  extern __shared__ float strip[];                         // [n_rows][T + halo]
   __shared__ float red[PBSED_MAX_TAPS + 1][256];
   const int n = threadIdx.x % COUT, rl = threadIdx.x / COUT;
   const bool affine = scale != nullptr;
   const float sc = affine ? __ldg(scale) : 1.f, sh = affine ? __ldg(shift) : 0.f;
+  const int LD = p.T + halo;
   float acc[PBSED_MAX_TAPS];
 #pragma unroll
   for (int i = 0; i < PBSED_MAX_TAPS; ++i) acc[i] = 0.f;
@@ -77,6 +81,12 @@ conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* 
     const int b = g / p.F_out, fo = g % p.F_out;
     const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
     const int len_out = mask_out ? len_b : p.T;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_rows * LD; i += 256) {
+      const int r = i / LD, tt = i % LD;
+      strip[i] = cin1_load(in, p, b, fo + df_min + r, tt + dt_min, len_b, sc, sh, affine);
+    }
+    __syncthreads();
     const float* z = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + n;
     for (int t = rl; t < len_out; t += RL) {
       const float dz = __ldg(z + (long long)t * p.out_stride);
@@ -84,7 +94,7 @@ conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* 
 #pragma unroll
       for (int tap = 0; tap < PBSED_MAX_TAPS; ++tap) {
         if (tap < p.ntaps)
-          acc[tap] = fmaf(dz, cin1_load(in, p, b, fo + p.df[tap], t + p.dt[tap], len_b, sc, sh, affine), acc[tap]);
+          acc[tap] = fmaf(dz, strip[(p.df[tap] - df_min) * LD + t + p.dt[tap] - dt_min], acc[tap]);
       }
     }
   }
@@ -137,12 +147,29 @@ int conv_cin1_wgrad_dispatch(const pbsed_tapgemm_desc* d, const float* in, const
   if (!cin1_ok(d)) return 0;
   Cin1Params p;
   cin1_fill(d, p);
+  if (p.T > CIN1_TMAX) return 0;
+  int df_min = 0, df_max = 0, dt_min = 0, dt_max = 0;
+  for (int i = 0; i < p.ntaps; ++i) {
+    df_min = p.df[i] < df_min ? p.df[i] : df_min; df_max = p.df[i] > df_max ? p.df[i] : df_max;
+    dt_min = p.dt[i] < dt_min ? p.dt[i] : dt_min; dt_max = p.dt[i] > dt_max ? p.dt[i] : dt_max;
+  }
+  const int n_rows = df_max - df_min + 1, halo = dt_max - dt_min;
+  const size_t smem = (size_t)n_rows * (p.T + halo) * sizeof(float);
+  if (smem > 160 * 1024) return 0;
   const int total = p.B * p.F_out;
   int gpc = cdiv(total, 148 * 8);
   if (gpc < 1) gpc = 1;
   dim3 grid(cdiv(total, gpc));
-  if (p.Cout == 16) conv_cin1_wgrad_kernel<16><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc);
-  else              conv_cin1_wgrad_kernel<32><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc);
+  cudaError_t e;
+  if (p.Cout == 16) {
+    e = cudaFuncSetAttribute(conv_cin1_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_cin1_wgrad_kernel<16><<<grid, 256, smem, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc, df_min, n_rows, dt_min, halo);
+  } else {
+    e = cudaFuncSetAttribute(conv_cin1_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    conv_cin1_wgrad_kernel<32><<<grid, 256, smem, st>>>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc, df_min, n_rows, dt_min, halo);
+  }
   *handled = 1;
   return pbsed_after_launch();
 }

@@ -64,6 +64,75 @@ colreduce_kernel(const float* __restrict__ a, const float* __restrict__ x, int F
   }
 }
 
+// float4 variant (C % 4 == 0, C <= 1024): thread = (row lane, channel quad); 4 independent rows in flight
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce4_kernel(const float* __restrict__ a, const float* __restrict__ x, int F, int T, int C,
+                  int per_f, const int* __restrict__ seq_len, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, double* __restrict__ out, int t_chunk) {
+  __shared__ float4 red[2][256];
+  const int tid = threadIdx.x;
+  const int g = blockIdx.x;
+  const int b = g / F, f = g % F;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+  const int t0 = blockIdx.y * t_chunk;
+  const int t1 = min(t0 + t_chunk, len_b);
+  if (t0 >= t1) return;
+  const int C4 = C >> 2;
+  const int rl = 256 / C4;
+  const int lane_r = tid / C4, q = tid % C4;
+  const int idx_base = (per_f ? f * C : 0) + q * 4;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (lane_r < rl) {
+    float4 mu = s0, rs = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == 1) {
+      mu = __ldg(reinterpret_cast<const float4*>(mean + idx_base));
+      rs = __ldg(reinterpret_cast<const float4*>(rstd + idx_base));
+    }
+    const float4* ap = reinterpret_cast<const float4*>(a + (long long)g * T * C) + q;
+    const float4* xp = MODE == 1 ? reinterpret_cast<const float4*>(x + (long long)g * T * C) + q : nullptr;
+    for (int t = t0 + lane_r; t < t1; t += 4 * rl) {
+      float4 v[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int tt = t + k * rl;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f); w[k] = mu;
+        if (tt < t1) {
+          v[k] = __ldg(ap + (long long)tt * C4);
+          if (MODE == 1) w[k] = __ldg(xp + (long long)tt * C4);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (MODE == 0) {
+          s0.x += v[k].x; s0.y += v[k].y; s0.z += v[k].z; s0.w += v[k].w;
+          s1.x = fmaf(v[k].x, v[k].x, s1.x); s1.y = fmaf(v[k].y, v[k].y, s1.y);
+          s1.z = fmaf(v[k].z, v[k].z, s1.z); s1.w = fmaf(v[k].w, v[k].w, s1.w);
+        } else {
+          s0.x += v[k].x; s0.y += v[k].y; s0.z += v[k].z; s0.w += v[k].w;
+          s1.x = fmaf(v[k].x, (w[k].x - mu.x) * rs.x, s1.x); s1.y = fmaf(v[k].y, (w[k].y - mu.y) * rs.y, s1.y);
+          s1.z = fmaf(v[k].z, (w[k].z - mu.z) * rs.z, s1.z); s1.w = fmaf(v[k].w, (w[k].w - mu.w) * rs.w, s1.w);
+        }
+      }
+    }
+  }
+  red[0][tid] = s0; red[1][tid] = s1;
+  __syncthreads();
+  if (lane_r == 0) {
+    double d0[4] = {0., 0., 0., 0.}, d1[4] = {0., 0., 0., 0.};
+    for (int r = 0; r < rl; ++r) {
+      const float4 u0 = red[0][r * C4 + q], u1 = red[1][r * C4 + q];
+      d0[0] += u0.x; d0[1] += u0.y; d0[2] += u0.z; d0[3] += u0.w;
+      d1[0] += u1.x; d1[1] += u1.y; d1[2] += u1.z; d1[3] += u1.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(out + 2 * (idx_base + k), d0[k]);
+      atomicAdd(out + 2 * (idx_base + k) + 1, d1[k]);
+    }
+  }
+}
+
 static int stats_t_chunk(int B, int F, int T) {
   // enough CTAs to fill 148 SMs a few times over, chunks of >= 32 frames
   long long groups = (long long)B * F;
@@ -79,8 +148,12 @@ extern "C" int pbsed_channel_stats(const float* x, int B, int F, int T, int C, i
   if (!x || !stats || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
   const int tc = stats_t_chunk(B, F, T);
   dim3 grid(B * F, cdiv(T, tc));
-  colreduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
-                                                              nullptr, nullptr, stats, tc);
+  if ((C & 3) == 0 && C <= 1024 && (((uintptr_t)x) & 15) == 0)
+    colreduce4_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
+                                                                 nullptr, nullptr, stats, tc);
+  else
+    colreduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
+                                                                nullptr, nullptr, stats, tc);
   return pbsed_after_launch();
 }
 
@@ -90,8 +163,12 @@ extern "C" int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int 
   if (!g || !x || !sums || !save_mean || !save_rstd || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
   const int tc = stats_t_chunk(B, F, T);
   dim3 grid(B * F, cdiv(T, tc));
-  colreduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
-                                                              save_mean, save_rstd, sums, tc);
+  if ((C & 3) == 0 && C <= 1024 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)save_mean) | ((uintptr_t)save_rstd)) & 15) == 0)
+    colreduce4_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
+                                                                 save_mean, save_rstd, sums, tc);
+  else
+    colreduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
+                                                                save_mean, save_rstd, sums, tc);
   return pbsed_after_launch();
 }
 
@@ -194,6 +271,41 @@ norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, 
   }
 }
 
+__global__ void __launch_bounds__(256)
+norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ x, int F, int T, int C4,
+                       int per_f, const int* __restrict__ seq_len, const float4* __restrict__ mean,
+                       const float4* __restrict__ rstd, const float4* __restrict__ gamma,
+                       const double* __restrict__ sums, float inv_n, float4* __restrict__ dx,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const int q = (int)(i % C4);
+    const long long row = i / C4;
+    const int t = (int)(row % T);
+    const long long gq = row / T;
+    const int f = (int)(gq % F), b = (int)(gq / F);
+    const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len_b) {
+      const int i4 = (per_f ? f * C4 : 0) + q;
+      const float4 rs = __ldg(rstd + i4), mu = __ldg(mean + i4), xv = __ldg(x + i), gv = __ldg(g + i);
+      const float4 ga = gamma ? __ldg(gamma + i4) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const double* sp = sums + 8 * (long long)i4;
+      r.x = ga.x * rs.x * (gv.x - (float)sp[0] * inv_n - (xv.x - mu.x) * rs.x * ((float)sp[1] * inv_n));
+      r.y = ga.y * rs.y * (gv.y - (float)sp[2] * inv_n - (xv.y - mu.y) * rs.y * ((float)sp[3] * inv_n));
+      r.z = ga.z * rs.z * (gv.z - (float)sp[4] * inv_n - (xv.z - mu.z) * rs.z * ((float)sp[5] * inv_n));
+      r.w = ga.w * rs.w * (gv.w - (float)sp[6] * inv_n - (xv.w - mu.w) * rs.w * ((float)sp[7] * inv_n));
+    }
+    dx[i] = r;
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int j = threadIdx.x; j < nch; j += blockDim.x) {
+      dbeta[j] += (float)sums[2 * j];
+      dgamma[j] += (float)sums[2 * j + 1];
+    }
+  }
+}
+
 extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F, int T, int C,
                                     int per_f, const int* seq_len, const float* save_mean,
                                     const float* save_rstd, const float* gamma, const double* sums,
@@ -203,6 +315,18 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
   if ((dgamma == nullptr) != (dbeta == nullptr)) return PBSED_EINVAL;
   const long long total = (long long)B * F * T * C;
   const int nch = per_f ? F * C : C;
+  if ((C & 3) == 0 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
+                        ((uintptr_t)save_rstd) | ((uintptr_t)gamma)) & 15) == 0) {
+    const long long total4 = total / 4;
+    int blocks4 = (int)((total4 + 255) / 256);
+    if (blocks4 > 148 * 16) blocks4 = 148 * 16;
+    norm_bwd_apply4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x), F, T, C / 4, per_f, seq_len,
+        reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
+        reinterpret_cast<const float4*>(gamma), sums, (float)(1.0 / count), reinterpret_cast<float4*>(dx),
+        dgamma, dbeta, total4, nch);
+    return pbsed_after_launch();
+  }
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   norm_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -254,6 +378,42 @@ maxpool_f_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ i
   }
 }
 
+// pool == 2, C % 4 == 0: float4 in, float4 out, uchar4 argmax
+__global__ void __launch_bounds__(256)
+maxpool2_f4_kernel(const float4* __restrict__ x, int Fo, long long TC4, float4* __restrict__ y,
+                   uchar4* __restrict__ idx, long long total4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long tc = i % TC4, gq = i / TC4;         // gq = b * Fo + fo
+    const float4 a = __ldg(x + (2 * gq) * TC4 + tc), c = __ldg(x + (2 * gq + 1) * TC4 + tc);
+    float4 r; uchar4 k;
+    k.x = (c.x > a.x || c.x != c.x) ? 1 : 0; r.x = k.x ? c.x : a.x;
+    k.y = (c.y > a.y || c.y != c.y) ? 1 : 0; r.y = k.y ? c.y : a.y;
+    k.z = (c.z > a.z || c.z != c.z) ? 1 : 0; r.z = k.z ? c.z : a.z;
+    k.w = (c.w > a.w || c.w != c.w) ? 1 : 0; r.w = k.w ? c.w : a.w;
+    y[i] = r;
+    if (idx) idx[i] = k;
+  }
+}
+__global__ void __launch_bounds__(256)
+maxpool2_f4_bwd_kernel(const float4* __restrict__ dy, const uchar4* __restrict__ idx, long long TC4,
+                       float4* __restrict__ dx, long long total4_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4_out; i += stride) {
+    const long long tc = i % TC4, gq = i / TC4;
+    const float4 g = __ldg(dy + i);
+    const uchar4 k = idx[i];
+    float4 lo = z, hi = z;
+    if (k.x) hi.x = g.x; else lo.x = g.x;
+    if (k.y) hi.y = g.y; else lo.y = g.y;
+    if (k.z) hi.z = g.z; else lo.z = g.z;
+    if (k.w) hi.w = g.w; else lo.w = g.w;
+    dx[(2 * gq) * TC4 + tc] = lo;
+    dx[(2 * gq + 1) * TC4 + tc] = hi;
+  }
+}
+
 static int ew_blocks(long long total) {
   long long b = (total + 255) / 256;
   if (b > 148LL * 16) b = 148LL * 16;
@@ -265,6 +425,12 @@ extern "C" int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int p
                                uint8_t* idx, void* stream) {
   if (!x || !y || pool < 1 || pool > 255 || F / pool < 1) return PBSED_EINVAL;
   const long long total = (long long)B * (F / pool) * T * C;
+  if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)idx)) & 15) == 0) {
+    maxpool2_f4_kernel<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
+        reinterpret_cast<uchar4*>(idx), total / 4);
+    return pbsed_after_launch();
+  }
   maxpool_f_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, F, (long long)T * C, pool, y, idx, total);
   return pbsed_after_launch();
 }
@@ -273,6 +439,13 @@ extern "C" int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, i
                                    int pool, float* dx, void* stream) {
   if (!dy || !idx || !dx || pool < 1 || F / pool < 1) return PBSED_EINVAL;
   const long long total = (long long)B * F * T * C;
+  if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)dx) | ((uintptr_t)dy) | ((uintptr_t)idx)) & 15) == 0) {
+    const long long total4_out = total / 8;
+    maxpool2_f4_bwd_kernel<<<ew_blocks(total4_out), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const uchar4*>(idx), (long long)T * C / 4,
+        reinterpret_cast<float4*>(dx), total4_out);
+    return pbsed_after_launch();
+  }
   maxpool_f_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, idx, F, (long long)T * C, pool, dx, total);
   return pbsed_after_launch();
 }

@@ -221,6 +221,10 @@ int conv_cin1_wgrad_dispatch(const pbsed_tapgemm_desc* d, const float* in, const
                              const float* shift, const int* seq_len, const float* dout, int mask_out,
                              float* dW, float* dbias, cudaStream_t st, int* handled);
 
+int wgrad_small_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                         const float* shift, const int* seq_len, const float* dout, int mask_out,
+                         float* dW, float* dbias, cudaStream_t st, int* handled);
+
 extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                              const float* shift, const int* seq_len, const float* W,
                              const float* bias, float* out, const float* ep_src,
@@ -386,6 +390,8 @@ extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in,
   {
     int handled = 0;
     rc = conv_cin1_wgrad_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
+    if (handled || rc) return rc;
+    rc = wgrad_small_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
     if (handled || rc) return rc;
   }
   if (d->precision != 0) {

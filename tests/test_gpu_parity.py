@@ -62,7 +62,8 @@ def test_stft_logmel_matches_float64_oracle(S, kw, n_mels):
 
 # ------------------------------------------------------------------ K2 tap-GEMM
 @pytest.mark.parametrize('B,Cin,Cout,Fh,T,k', [(2, 1, 16, 12, 37, 3), (2, 16, 16, 8, 130, 3), (1, 11, 24, 6, 50, 3),
-                                                (2, 32, 64, 4, 129, 3), (1, 64, 256, 2, 70, 3)])
+                                                (2, 32, 64, 4, 129, 3), (1, 64, 256, 2, 70, 3),
+                                                (2, 16, 32, 5, 200, 3), (1, 32, 32, 3, 67, 3), (1, 128, 128, 2, 140, 3)])
 def test_conv2d_forward_backward_vs_torch(B, Cin, Cout, Fh, T, k):
     from pb_sed_b200 import ops
     from pb_sed_b200.modules import _Conv
