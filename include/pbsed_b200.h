@@ -100,14 +100,23 @@ typedef struct {
   long long w_tap_stride, w_sn, w_sc;
   int in_stride;     /* row stride of `in` in floats  (0 -> Cin;  lets a GRU direction read its half of a (B,T,2H) map) */
   int out_stride;    /* row stride of `out` / `dout` / `ep_src` in floats (0 -> Cout) */
-  int precision;     /* 0 = exact fp32 FFMA; 1 = 3xTF32 tcgen05; 2 = bf16 tcgen05 (where supported) */
+  int precision;     /* 0 = exact fp32 FFMA; 1 = 3xTF32 tcgen05 (fp32-equivalent split) */
+  int no_input_mask; /* 1: seq_len does NOT zero the loaded operand (a bare conv reads its input unmasked,
+                        the reference masks inside Normalization only); seq_len still masks the fused
+                        statistics / epilogue */
 } pbsed_tapgemm_desc;
 
 int pbsed_tapgemm(const pbsed_tapgemm_desc* d_host,
                   const float* in, const float* scale, const float* shift, const int* seq_len,
                   const float* W, const float* bias, float* out,
                   const float* ep_src, const float* ep_scale, const float* ep_shift,
+                  double* out_stats, const float* ep_mean, const float* ep_rstd, double* ep_sums,
                   void* workspace, long long workspace_bytes, void* stream);
+/* fused column reductions (all nullable; they save a full pass over the output map):
+ *   out_stats[idx][0..1] += sum / sum of squares of `out` over frames t < seq_len[b]
+ *                            (idx = n, or fo*Cout + n when per_f) -- the next layer's batch statistics
+ *   ep_sums[idx][0..1]   += sum out, sum out * (ep_src - ep_mean[idx]) * ep_rstd[idx]
+ *                            -- pass 1 of the batch-norm backward when this call is a data-gradient pass */
 /* bytes of caller-owned scratch the tensor-core path needs (pre-tiled hi/lo weight image);
  * 0 for precision 0.  A NULL / too small workspace with precision != 0 runs the exact-fp32 kernel. */
 long long pbsed_tapgemm_workspace_bytes(const pbsed_tapgemm_desc* d_host);

@@ -211,7 +211,8 @@ static int launch_fwd(const TapParams& p, const float* in, const float* scale, c
 int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                         const float* shift, const int* seq_len, const float* W, const float* bias,
                         float* out, const float* ep_src, const float* ep_scale,
-                        const float* ep_shift, void* workspace, long long ws_bytes,
+                        const float* ep_shift, double* out_stats, const float* ep_mean,
+                        const float* ep_rstd, double* ep_sums, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled);
 
 int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
@@ -225,26 +226,15 @@ int wgrad_small_dispatch(const pbsed_tapgemm_desc* d, const float* in, const flo
                          const float* shift, const int* seq_len, const float* dout, int mask_out,
                          float* dW, float* dbias, cudaStream_t st, int* handled);
 
-extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
-                             const float* shift, const int* seq_len, const float* W,
-                             const float* bias, float* out, const float* ep_src,
-                             const float* ep_scale, const float* ep_shift, void* workspace,
-                             long long workspace_bytes, void* stream) {
-  TapParams p;
-  int rc = fill_params(d, p);
-  if (rc) return rc;
-  if (!in || !W || !out) return PBSED_EINVAL;
-  if ((scale == nullptr) != (shift == nullptr)) return PBSED_EINVAL;
-  cudaStream_t st = (cudaStream_t)stream;
+static int tapgemm_plain(const pbsed_tapgemm_desc* d, const TapParams& p, const float* in,
+                         const float* scale, const float* shift, const int* seq_len,
+                         const int* ep_seq_len, const float* W, const float* bias, float* out,
+                         const float* ep_src, const float* ep_scale, const float* ep_shift,
+                         cudaStream_t st) {
+  int rc;
   {
     int handled = 0;
     rc = conv_cin1_fwd_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, st, &handled);
-    if (handled || rc) return rc;
-  }
-  if (d->precision != 0) {
-    int handled = 0;
-    rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
-                             workspace, workspace_bytes, st, &handled);
     if (handled || rc) return rc;
   }
   if (p.Cout <= 16)
@@ -252,6 +242,39 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   if (p.Cout <= 32)
     return launch_fwd<128, 32, 16, 8, 4>(p, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
   return launch_fwd<128, 64, 16, 8, 8>(p, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
+}
+
+extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                             const float* shift, const int* seq_len, const float* W,
+                             const float* bias, float* out, const float* ep_src,
+                             const float* ep_scale, const float* ep_shift, double* out_stats,
+                             const float* ep_mean, const float* ep_rstd, double* ep_sums,
+                             void* workspace, long long workspace_bytes, void* stream) {
+  TapParams p;
+  int rc = fill_params(d, p);
+  if (rc) return rc;
+  if (!in || !W || !out) return PBSED_EINVAL;
+  if ((scale == nullptr) != (shift == nullptr)) return PBSED_EINVAL;
+  if (ep_sums && (!ep_src || !ep_mean || !ep_rstd)) return PBSED_EINVAL;
+  if ((out_stats || ep_sums) && p.out_stride != p.Cout) return PBSED_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* load_seq = d->no_input_mask ? nullptr : seq_len;
+  if (d->precision != 0) {
+    int handled = 0;
+    rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
+                             out_stats, ep_mean, ep_rstd, ep_sums, workspace, workspace_bytes, st, &handled);
+    if (handled || rc) return rc;
+  }
+  rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
+  if (rc) return rc;
+  // kernels without fused reductions: run them as separate passes over the finished map
+  if (out_stats) {
+    rc = pbsed_channel_stats(out, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, out_stats, stream);
+    if (rc) return rc;
+  }
+  if (ep_sums)
+    rc = pbsed_norm_bwd_reduce(out, ep_src, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, ep_mean, ep_rstd, ep_sums, stream);
+  return rc;
 }
 
 // ---------------------------------------------------------------- weight gradient

@@ -153,6 +153,7 @@ wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn
 struct __align__(16) SmemCtl {
   uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], acc_full;
   uint32_t tmem_base;
+  float colacc[2][NSLICE];      // epilogue column sums of one row tile
 };
 
 template <int MT>
@@ -162,7 +163,9 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
                   const float* __restrict__ img, const float* __restrict__ bias,
                   float* __restrict__ out, const float* __restrict__ ep_src,
                   const float* __restrict__ ep_scale, const float* __restrict__ ep_shift,
-                  int t_super) {
+                  double* __restrict__ out_stats, const float* __restrict__ ep_mean,
+                  const float* __restrict__ ep_rstd, double* __restrict__ ep_sums,
+                  const int* __restrict__ load_seq_len, int t_super, int ctl_pad) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int N = p.N;
   constexpr int RMAX = MT * TILE_M + 2 * HALO;         // strip rows
@@ -172,7 +175,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   const uint32_t B_STAGE = 2 * B_PART;
   uint8_t* a_smem = smem_raw;
   uint8_t* b_smem = smem_raw + NA * A_STAGE;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(b_smem + NB * B_STAGE);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(b_smem + NB * B_STAGE + ctl_pad);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x % p.n_slices, st = blockIdx.x / p.n_slices;
@@ -180,7 +183,8 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   const int t0 = st * (MT * TILE_M);
   const int rows_here = min(p.T - t0, MT * TILE_M);
   const int mt_count = (rows_here + TILE_M - 1) / TILE_M;
-  const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;            // epilogue / statistics mask
+  const int len_in = load_seq_len ? min(__ldg(load_seq_len + b), p.T) : p.T;  // operand-load mask
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < mt_count * N) tmem_cols <<= 1;
 
@@ -191,6 +195,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (tid < NSLICE) { ctl->colacc[0][tid] = 0.f; ctl->colacc[1][tid] = 0.f; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -225,7 +230,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           for (int u = 0; u < U; ++u) {
             const int r = r0 + 32 * u, t = t0 + r - HALO;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows && t >= 0 && t < len_b)
+            if (r < nrows && t >= 0 && t < len_in)
               v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * p.in_stride));
           }
 #pragma unroll
@@ -233,7 +238,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
             const int r = r0 + 32 * u, t = t0 + r - HALO;
             if (r >= nrows) break;
             float4 x = v[u];
-            if (t >= 0 && t < len_b) {
+            if (t >= 0 && t < len_in) {
               if (scale) {
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
@@ -257,44 +262,88 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
       }
     }
     // ============================== epilogue ==============================
+    // TMEM -> registers (thread = frame) -> bias / ReLU-mask -> shared-memory tile -> (a) row-contiguous
+    // float4 stores, (b) per-channel column sums for the fused statistics.  The operand rings are idle
+    // once acc_full fires, so the tile(s) reuse that shared memory.
     mbar_wait(&ctl->acc_full, 0);
     tc_fence_after();
     const long long orow0 = ((long long)b * p.F_out + fo) * p.T;
     const int n0 = slice * N;
     const int ep_base = (p.per_f ? fo * p.Cout : 0) + n0;
+    const int LDT = N + 4;
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    float* tile2 = tile + TILE_M * LDT;
+    const int nq = N >> 2;
     for (int mt = 0; mt < mt_count; ++mt) {
-      const int t = t0 + mt * TILE_M + warp * 32 + lane;
+      const int row = warp * 32 + lane;
+      const int t = t0 + mt * TILE_M + row;
       for (int cc = 0; cc < N; cc += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + cc), v);
-        if (t < p.T) {
-          float* dst = out + (orow0 + t) * p.out_stride + n0 + cc;
-          const float* es = ep_src ? ep_src + (orow0 + t) * p.out_stride + n0 + cc : nullptr;
+        const float* es = (ep_src && t < p.T) ? ep_src + (orow0 + t) * p.out_stride + n0 + cc : nullptr;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + j));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (es) {
-              float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (t < len_b) {
-                s = __ldg(reinterpret_cast<const float4*>(es + j));
-                if (ep_scale) {
-                  const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
-                  const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
-                  s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
-                  s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
-                }
-              }
-              o.x = s.x > 0.f ? o.x : 0.f; o.y = s.y > 0.f ? o.y : 0.f;
-              o.z = s.z > 0.f ? o.z : 0.f; o.w = s.w > 0.f ? o.w : 0.f;
-            }
-            *reinterpret_cast<float4*>(dst + j) = o;
+        for (int j = 0; j < 16; j += 4) {
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          float4 o2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + j));
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
+          if (ep_src) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), s = x;
+            if (es && t < len_b) {
+              x = __ldg(reinterpret_cast<const float4*>(es + j));
+              s = x;
+              if (ep_scale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
+                s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
+                s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
+              }
+            }
+            o.x = s.x > 0.f ? o.x : 0.f; o.y = s.y > 0.f ? o.y : 0.f;
+            o.z = s.z > 0.f ? o.z : 0.f; o.w = s.w > 0.f ? o.w : 0.f;
+            if (ep_sums) {
+              const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + ep_base + cc + j));
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + ep_base + cc + j));
+              o2.x = o.x * (x.x - mu.x) * rs.x; o2.y = o.y * (x.y - mu.y) * rs.y;
+              o2.z = o.z * (x.z - mu.z) * rs.z; o2.w = o.w * (x.w - mu.w) * rs.w;
+            }
+          }
+          *reinterpret_cast<float4*>(tile + row * LDT + cc + j) = o;
+          if (ep_sums) *reinterpret_cast<float4*>(tile2 + row * LDT + cc + j) = o2;
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tbase = t0 + mt * TILE_M;
+      for (int idx = tid; idx < TILE_M * nq; idx += 128) {
+        const int r = idx / nq, q = idx - r * nq;
+        if (tbase + r < p.T)
+          *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) =
+              *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
+      }
+      if (out_stats || ep_sums) {
+        // all 128 threads: (row group rg, column c); partial sums meet in shared-memory atomics and
+        // are flushed to the global double accumulators ONCE per CTA (same-address fp64 atomics from
+        // hundreds of CTAs serialise in L2)
+        const int valid = max(0, min(TILE_M, len_b - tbase));
+        const int RG = TILE_M / N;                         // N in {16,32,64,128} -> 8,4,2,1 row groups
+        const int c = tid % N, rg = tid / N;
+        float s0 = 0.f, s1 = 0.f;
+        if (out_stats) {
+          for (int r = rg; r < valid; r += RG) { const float x = tile[r * LDT + c]; s0 += x; s1 = fmaf(x, x, s1); }
+        } else {
+          for (int r = rg; r < valid; r += RG) { s0 += tile[r * LDT + c]; s1 += tile2[r * LDT + c]; }
+        }
+        atomicAdd(&ctl->colacc[0][c], s0);
+        atomicAdd(&ctl->colacc[1][c], s1);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if ((out_stats || ep_sums) && tid < N) {
+      double* dst = (out_stats ? out_stats : ep_sums) + 2 * (ep_base + tid);
+      atomicAdd(dst, (double)ctl->colacc[0][tid]);
+      atomicAdd(dst + 1, (double)ctl->colacc[1][tid]);
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -668,13 +717,16 @@ static bool tc_eligible(const pbsed_tapgemm_desc* d) {
 int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                         const float* shift, const int* seq_len, const float* W, const float* bias,
                         float* out, const float* ep_src, const float* ep_scale,
-                        const float* ep_shift, void* workspace, long long ws_bytes,
+                        const float* ep_shift, double* out_stats, const float* ep_mean,
+                        const float* ep_rstd, double* ep_sums, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled) {
   *handled = 0;
+  if (out_stats && ep_sums) return 0;
   if (d->precision != 1 || !workspace || !tc_eligible(d)) return 0;
   if (ws_bytes < pbsed_tapgemm_workspace_bytes(d)) return PBSED_EWORKSPACE;
   if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale |
-        (uintptr_t)shift | (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift) & 15) != 0)
+        (uintptr_t)shift | (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift |
+        (uintptr_t)ep_mean | (uintptr_t)ep_rstd) & 15) != 0)
     return 0;                                   // unaligned views: exact-fp32 kernel handles them
   TcParams p = {};
   p.B = d->B; p.F_in = d->F_in; p.F_out = d->F_out; p.T = d->T; p.Cin = d->Cin; p.Cout = d->Cout;
@@ -705,8 +757,10 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   // row tiles per CTA: big N wants many rows per weight fetch, small N wants co-resident CTAs
   int mt = p.N >= 128 ? 4 : (p.N >= 64 ? 2 : 1);
   while (mt > 1 && (long long)p.B * p.F_out * cdiv(p.T, mt * TILE_M) * p.n_slices < 2 * 148) mt >>= 1;
-  const size_t smem = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)NB * 2 * KCH * p.N * 16 +
-                     sizeof(SmemCtl) + 128;
+  size_t rings = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)NB * 2 * KCH * p.N * 16;
+  const size_t tiles = (size_t)(ep_sums ? 2 : 1) * TILE_M * (p.N + 4) * sizeof(float);   // epilogue staging
+  const size_t pad = tiles > rings ? ((tiles - rings + 127) / 128) * 128 : 0;
+  const size_t smem = rings + pad + sizeof(SmemCtl) + 128;
   const int t_super = cdiv(p.T, mt * TILE_M);
   dim3 grid(t_super * p.n_slices, p.F_out, p.B);
   if (grid.y > 65535 || grid.z > 65535) return 0;
@@ -715,7 +769,8 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                 \
   tapgemm_tc_kernel<MTV><<<grid, 192, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
-                                                  ep_scale, ep_shift, t_super);
+                                                  ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
+                                                  d->no_input_mask ? nullptr : seq_len, t_super, (int)pad);
   if (mt == 4) { PBSED_TC_LAUNCH(4) } else if (mt == 2) { PBSED_TC_LAUNCH(2) } else { PBSED_TC_LAUNCH(1) }
 #undef PBSED_TC_LAUNCH
   *handled = 1;

@@ -332,9 +332,20 @@ class _CNN(nn.Module):
             return int(p[0])
         raise NotImplementedError('1-D pooling is not on the hot path')
 
-    def forward_native(self, x, seq):
-        """x (B,F,T,C) native -> (B,F',T,C')."""
+    def _input_norm(self, i):
+        """the Normalization applied to layer i's INPUT (fused into its operand load), or None."""
+        if self.pre_activation:
+            return self.norms[i]
+        return self.norms[i - 1] if i > 0 else None
+
+    def forward_native(self, x, seq, stats_in=None, next_stats=None):
+        """x (B,F,T,C) native -> (B,F',T,C').
+
+        stats_in: batch statistics of x already produced by the previous stack's last conv.
+        next_stats: None, or 'c' / 'fc' -- also return the statistics of the output (per channel /
+        per (f, c)) for a following stack's first norm; then the result is (y, stats)."""
         n = len(self.convs)
+        stats = stats_in
         for i, conv in enumerate(self.convs):
             B, F_in, T, _ = x.shape
             if self.pre_activation:
@@ -345,18 +356,28 @@ class _CNN(nn.Module):
                 relu = i > 0
             fh = conv.flatten_height
             assert F_in == fh or fh == 1, (F_in, fh)
+            # does the consumer of this layer's output normalise with batch statistics?  then the conv
+            # epilogue accumulates them (pooled layers: the statistics are of the pooled map -> own pass)
+            if i + 1 < n:
+                want, want_pf = self.training and self._input_norm(i + 1) is not None, False
+            else:
+                want, want_pf = self.training and next_stats is not None, next_stats == 'fc'
             cfg = dict(F_in=F_in, F_out=1 if fh > 1 else F_in, taps=conv.taps, relu=relu,
                        per_f=fh > 1, pool=self._pool(self.pool_sizes[i]), norm=norm is not None,
                        eps=norm.eps if norm is not None else 0.,
                        momentum=norm.momentum if norm is not None else 0.,
-                       training=self.training)
+                       training=self.training, want_stats=want, stats_per_f=want_pf)
             if norm is not None:
-                x = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, norm.scale, norm.shift,
-                                          norm.running_mean, norm.running_power,
-                                          norm.num_tracked_values, seq, cfg)
+                x, stats = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, norm.scale, norm.shift,
+                                                 norm.running_mean, norm.running_power,
+                                                 norm.num_tracked_values, seq, cfg, stats)
             else:
-                x = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, None, None, None, None, None,
-                                          seq, cfg)
+                x, stats = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, None, None, None, None, None,
+                                                 seq, cfg, None)
+            if stats.numel() == 0:
+                stats = None
+        if next_stats is not None:
+            return x, stats
         return x
 
     def forward(self, x, seq_len=None):
@@ -413,8 +434,14 @@ class CNN(nn.Module):
         if self.conditional_dims:
             cond = condition.reshape(condition.shape[0], -1)
             x = ops.ConcatCondFn.apply(x, cond)
-        x = self.cnn_2d.forward_native(x, seq)
-        x = self.cnn_1d.forward_native(x, seq)            # (B,1,T,D)
+        # the first cnn_1d norm is indexed per (f, c) of the cnn_2d output: its statistics come out of
+        # the last cnn_2d conv's epilogue
+        want = 'fc' if (self.training and self.cnn_1d._input_norm(0) is not None) else None
+        if want:
+            x, stats = self.cnn_2d.forward_native(x, seq, next_stats=want)
+        else:
+            x, stats = self.cnn_2d.forward_native(x, seq), None
+        x = self.cnn_1d.forward_native(x, seq, stats_in=stats)            # (B,1,T,D)
         return x.squeeze(1)
 
     def forward(self, x, seq_len=None, condition=None):

@@ -106,7 +106,7 @@ def from_native(x):
 
 # ------------------------------------------------------------------ raw kernels
 def make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=False, per_f=False, transpose_w=False,
-              in_stride=0, out_stride=0, precision=None):
+              in_stride=0, out_stride=0, precision=None, no_input_mask=False):
     d = TapGemmDesc()
     d.B, d.F_in, d.F_out, d.T, d.Cin, d.Cout = B, F_in, F_out, T, Cin, Cout
     d.ntaps = len(taps)
@@ -121,11 +121,12 @@ def make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=False, per_f=False, trans
         d.w_sn, d.w_sc = Cin, 1
     d.in_stride, d.out_stride = in_stride, out_stride
     d.precision = _default_precision if precision is None else precision
+    d.no_input_mask = int(no_input_mask)
     return d
 
 
 def tapgemm(x, W, bias, desc, scale=None, shift=None, seq=None, ep_src=None, ep_scale=None,
-            ep_shift=None, out=None, x_ptr=None):
+            ep_shift=None, out=None, x_ptr=None, out_stats=None, ep_mean=None, ep_rstd=None, ep_sums=None):
     rows = desc.B * desc.F_out * desc.T
     if out is None:
         out = torch.empty((rows, desc.Cout), device=W.device, dtype=torch.float32)
@@ -135,7 +136,8 @@ def tapgemm(x, W, bias, desc, scale=None, shift=None, seq=None, ep_src=None, ep_
         ws = torch.empty(ws_bytes, device=W.device, dtype=torch.uint8)
     call('pbsed_tapgemm', ctypes.byref(desc), x_ptr if x_ptr is not None else _ptr(x), _ptr(scale),
          _ptr(shift), seq.ptr if seq is not None else None, _ptr(W), _ptr(bias), _ptr(out),
-         _ptr(ep_src), _ptr(ep_scale), _ptr(ep_shift), _ptr(ws), ws_bytes, _stream())
+         _ptr(ep_src), _ptr(ep_scale), _ptr(ep_shift), _ptr(out_stats), _ptr(ep_mean), _ptr(ep_rstd),
+         _ptr(ep_sums), _ptr(ws), ws_bytes, _stream())
     return out
 
 
@@ -169,7 +171,10 @@ class ConvLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, rmean, rpower, ntracked, seq, cfg):
+    def forward(ctx, x, weight, bias, gamma, beta, rmean, rpower, ntracked, seq, cfg, stats_in=None):
+        """returns (y, stats_out): stats_out = (Cout[*F_out], 2) float64 sum / sum-of-squares of y over
+        valid frames when cfg['want_stats'] (fused into the conv epilogue), else an empty tensor.
+        stats_in: the same quantity for x, produced by the previous layer (skips the statistics pass)."""
         x = _f32c(x)
         B, F_in, T, Cin = x.shape
         ntaps, Cout, Cin_w = weight.shape
@@ -183,9 +188,12 @@ class ConvLayerFn(torch.autograd.Function):
             scale = torch.empty(nch, device=x.device)
             shift = torch.empty(nch, device=x.device)
             if cfg['training']:
-                stats = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
-                call('pbsed_channel_stats', _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                     _ptr(stats), _stream())
+                if stats_in is not None and stats_in.numel() == 2 * nch:
+                    stats = stats_in
+                else:
+                    stats = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
+                    call('pbsed_channel_stats', _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                         _ptr(stats), _stream())
                 smean = torch.empty(nch, device=x.device)
                 srstd = torch.empty(nch, device=x.device)
                 call('pbsed_norm_finalize', _ptr(stats), count, nch, _ptr(gamma), _ptr(beta),
@@ -195,11 +203,24 @@ class ConvLayerFn(torch.autograd.Function):
                 call('pbsed_norm_finalize', None, 1.0, nch, _ptr(gamma), _ptr(beta), cfg['eps'],
                      cfg['momentum'], 0, _ptr(rmean), _ptr(rpower), _ptr(ntracked), _ptr(scale),
                      _ptr(shift), None, None, _stream())
-        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f)
         # the reference masks padded frames inside Normalization only: a bare conv (layer 0, whose
         # tag-condition channels are NOT zero at padded frames) reads its input unmasked
-        load_seq = seq if cfg['norm'] else None
-        z = tapgemm(x, weight, bias, desc, scale, shift, load_seq).view(B, F_out, T, Cout)
+        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
+                         no_input_mask=not cfg['norm'])
+        stats_out = None
+        if cfg.get('want_stats') and pool == 1:
+            sp = cfg.get('stats_per_f', False)
+            desc_s = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
+                               no_input_mask=not cfg['norm'])
+            stats_out = torch.zeros(((F_out if sp else 1) * Cout, 2), device=x.device, dtype=torch.float64)
+            if sp == per_f:
+                z = tapgemm(x, weight, bias, desc_s, scale, shift, seq, out_stats=stats_out)
+            else:      # statistics indexed differently from the load affine: separate pass
+                z = tapgemm(x, weight, bias, desc, scale, shift, seq)
+                call('pbsed_channel_stats', _ptr(z), B, F_out, T, Cout, int(sp), seq.ptr, _ptr(stats_out), _stream())
+            z = z.view(B, F_out, T, Cout)
+        else:
+            z = tapgemm(x, weight, bias, desc, scale, shift, seq).view(B, F_out, T, Cout)
         idx = None
         if pool > 1:
             y = torch.empty((B, F_out // pool, T, Cout), device=x.device)
@@ -210,10 +231,13 @@ class ConvLayerFn(torch.autograd.Function):
         ctx.cfg, ctx.seq, ctx.count = cfg, seq, count
         ctx.save_for_backward(x, weight, gamma, scale, shift, smean, srstd, idx)
         ctx.params = (weight, bias, gamma, beta)
-        return y
+        if stats_out is None:
+            stats_out = torch.empty(0, device=x.device, dtype=torch.float64)
+        ctx.mark_non_differentiable(stats_out)
+        return y, stats_out
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         x, weight, gamma, scale, shift, smean, srstd, idx = ctx.saved_tensors
         w_p, b_p, g_p, be_p = ctx.params
         cfg, seq = ctx.cfg, ctx.seq
@@ -235,16 +259,22 @@ class ConvLayerFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             rtaps = [(-df, -dt) for df, dt in cfg['taps']]
             ddesc = make_desc(B, F_out, F_in, T, Cout, Cin, rtaps, per_f=per_f, transpose_w=True)
-            use_ep = cfg['relu'] or cfg['norm']
-            g = tapgemm(dz, weight, None, ddesc, None, None, seq,
-                        ep_src=x if use_ep and cfg['relu'] else None,
-                        ep_scale=scale if cfg['relu'] else None,
-                        ep_shift=shift if cfg['relu'] else None).view(B, F_in, T, Cin)
-            if cfg['norm'] and cfg['training']:
+            train_norm = cfg['norm'] and cfg['training']
+            sums = None
+            fuse = train_norm and cfg['relu']          # batch-norm backward pass 1 rides in the dgrad epilogue
+            if train_norm:
                 nch = (F_in if per_f else 1) * Cin
                 sums = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
-                call('pbsed_norm_bwd_reduce', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                     _ptr(smean), _ptr(srstd), _ptr(sums), _stream())
+            g = tapgemm(dz, weight, None, ddesc, None, None, seq,
+                        ep_src=x if cfg['relu'] else None,
+                        ep_scale=scale if cfg['relu'] else None,
+                        ep_shift=shift if cfg['relu'] else None,
+                        ep_mean=smean if fuse else None, ep_rstd=srstd if fuse else None,
+                        ep_sums=sums if fuse else None).view(B, F_in, T, Cin)
+            if train_norm:
+                if not fuse:
+                    call('pbsed_norm_bwd_reduce', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                         _ptr(smean), _ptr(srstd), _ptr(sums), _stream())
                 dga, dg_ret = _grad_target(g_p)
                 dbe, dbe_ret = _grad_target(be_p)
                 call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
@@ -257,7 +287,7 @@ class ConvLayerFn(torch.autograd.Function):
                 dx = g * sc
             else:
                 dx = g
-        return dx, dW_ret, db_ret, dg_ret, dbe_ret, None, None, None, None, None
+        return dx, dW_ret, db_ret, dg_ret, dbe_ret, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------ GRU layer

@@ -16,13 +16,13 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert len(protos) >= 20
     for name in protos:
         assert hasattr(built_lib, name), name
-    assert built_lib.pbsed_abi_version() == 2
+    assert built_lib.pbsed_abi_version() == 3
     assert built_lib.pbsed_launch_count() >= 0
 
 
 def test_bad_arguments_return_einval_without_touching_the_gpu(built_lib):
     from pb_sed_b200 import _lib
-    assert built_lib.pbsed_tapgemm(None, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert built_lib.pbsed_tapgemm(None, None, None, None, None, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
     d = _lib.TapGemmDesc()
     d.B = d.F_in = d.F_out = d.T = d.Cin = d.Cout = 1
     d.ntaps = 99

@@ -76,7 +76,7 @@ def test_conv2d_forward_backward_vs_torch(B, Cin, Cout, Fh, T, k):
     seq = ops.SeqLen.make(None, B, T, DEV)
     cfg = dict(F_in=Fh, F_out=Fh, taps=conv.taps, relu=False, per_f=False, pool=1, norm=False,
                eps=0., momentum=0., training=True)
-    y = ops.ConvLayerFn.apply(xg, conv.weight, conv.bias, None, None, None, None, None, seq, cfg)
+    y, _ = ops.ConvLayerFn.apply(xg, conv.weight, conv.bias, None, None, None, None, None, seq, cfg)
     xr = x.clone().requires_grad_(True)
     w = conv._to_ref(conv.weight.detach().cpu()).requires_grad_(True)
     b = conv.bias.detach().cpu().clone().requires_grad_(True)
