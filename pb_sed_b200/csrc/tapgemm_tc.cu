@@ -156,8 +156,11 @@ struct __align__(16) SmemCtl {
   float colacc[2][NSLICE];      // epilogue column sums of one row tile
 };
 
+constexpr int FW_PROD = 256;              // producer / epilogue threads (warps 0-7); warp 8 = MMA, warp 9 = weights
+constexpr int FW_THREADS = FW_PROD + 64;
+
 template <int MT>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(FW_THREADS)
 tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const float* __restrict__ img, const float* __restrict__ bias,
@@ -189,12 +192,12 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   while ((int)tmem_cols < mt_count * N) tmem_cols <<= 1;
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&ctl->a_full[i], FW_PROD); mbar_init(&ctl->a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
     mbar_init(&ctl->acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (warp == FW_PROD / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
   if (tid < NSLICE) { ctl->colacc[0][tid] = 0.f; ctl->colacc[1][tid] = 0.f; }
   tc_fence_before();
   __syncthreads();
@@ -202,64 +205,78 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   const uint32_t tmem_base = ctl->tmem_base;
 
   // the stage list is identical for every role: (kb, group g) with a valid source row f = fo + df
-  if (warp < 4) {
+  if (warp < FW_PROD / 32) {
     // ============================== A producer ==============================
-    int it = 0;
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      for (int g = 0; g < p.ngroups; ++g) {
-        const int f_src = fo + p.g_df[g];
-        if (f_src < 0 || f_src >= p.F_in) continue;
-        const int slot = it % NA;
-        mbar_wait(&ctl->a_empty[slot], ((it / NA) & 1) ^ 1);
-        uint8_t* hi_base = a_smem + slot * A_STAGE;
-        uint8_t* lo_base = hi_base + A_PART;
-        const long long row0 = ((long long)b * p.F_in + f_src) * p.T;
-        const int c = tid & 3;                       // this thread's 16-byte k-chunk (idx & 3 is invariant)
-        const float* src = in + row0 * p.in_stride + kb * KB + c * 4;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (scale) {
-          const int aff = (p.per_f ? f_src * p.Cin : 0) + kb * KB + c * 4;
-          sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
-          sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
-        }
-        const int nrows = mt_count * TILE_M + 2 * HALO;
-        constexpr int U = 8;                         // independent 16-byte loads in flight per thread
-        for (int r0 = tid >> 2; r0 < nrows; r0 += 32 * U) {
-          float4 v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int r = r0 + 32 * u, t = t0 + r - HALO;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows && t >= 0 && t < len_in)
-              v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * p.in_stride));
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int r = r0 + 32 * u, t = t0 + r - HALO;
-            if (r >= nrows) break;
-            float4 x = v[u];
-            if (t >= 0 && t < len_in) {
-              if (scale) {
-                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
-                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-              }
-              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            }
-            float4 h;
-            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-            const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-            const uint32_t o = (uint32_t)(c * RMAX + r) * 16;
-            *reinterpret_cast<float4*>(hi_base + o) = h;
-            *reinterpret_cast<float4*>(lo_base + o) = l;
-          }
-        }
-        fence_async_smem();
-        mbar_arrive(&ctl->a_full[slot]);
-        ++it;
+    // software-pipelined across stages: the global loads of stage k+1 are issued (into registers)
+    // right after stage k has been written to shared memory, so their latency overlaps the wait for
+    // the MMA to release the next ring slot -- only the STORES are gated by a_empty.
+    constexpr int RSTEP = FW_PROD / 4;                        // frames covered by one pass of the threads
+    constexpr int U = (MT * TILE_M + 2 * HALO + RSTEP - 1) / RSTEP;
+    const int c = tid & 3;                                    // this thread's 16-byte k-chunk
+    const int r0 = tid >> 2;
+    const int nrows = mt_count * TILE_M + 2 * HALO;
+    float4 v[U];
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    int kb = 0, g = -1;
+    auto advance = [&]() -> bool {
+      while (true) {
+        if (++g == p.ngroups) { g = 0; ++kb; }
+        if (kb >= p.nkb) return false;
+        const int f = fo + p.g_df[g];
+        if (f >= 0 && f < p.F_in) return true;
       }
+    };
+    auto issue = [&]() {
+      const int f_src = fo + p.g_df[g];
+      const float* src = in + ((long long)b * p.F_in + f_src) * p.T * p.in_stride + kb * KB + c * 4;
+      if (scale) {
+        const int aff = (p.per_f ? f_src * p.Cin : 0) + kb * KB + c * 4;
+        sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
+        sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + RSTEP * u, t = t0 + r - HALO;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows && t >= 0 && t < len_in)
+          v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * p.in_stride));
+      }
+    };
+    bool have = advance();
+    if (have) issue();
+    int it = 0;
+    while (have) {
+      const int slot = it % NA;
+      mbar_wait(&ctl->a_empty[slot], ((it / NA) & 1) ^ 1);
+      uint8_t* hi_base = a_smem + slot * A_STAGE;
+      uint8_t* lo_base = hi_base + A_PART;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + RSTEP * u, t = t0 + r - HALO;
+        if (r >= nrows) break;
+        float4 x = v[u];
+        if (t >= 0 && t < len_in) {
+          if (scale) {
+            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+            x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+          }
+          if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        }
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        const uint32_t o = (uint32_t)(c * RMAX + r) * 16;
+        *reinterpret_cast<float4*>(hi_base + o) = h;
+        *reinterpret_cast<float4*>(lo_base + o) = l;
+      }
+      fence_async_smem();
+      mbar_arrive(&ctl->a_full[slot]);
+      ++it;
+      have = advance();
+      if (have) issue();
     }
     // ============================== epilogue ==============================
     // TMEM -> registers (thread = frame) -> bias / ReLU-mask -> shared-memory tile -> (a) row-contiguous
@@ -274,60 +291,71 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     float* tile = reinterpret_cast<float*>(smem_raw);
     float* tile2 = tile + TILE_M * LDT;
     const int nq = N >> 2;
+    const int lw = warp & 3, chalf = warp >> 2;             // TMEM lane quarter, column half
     for (int mt = 0; mt < mt_count; ++mt) {
-      const int row = warp * 32 + lane;
+      const int row = lw * 32 + lane;
       const int t = t0 + mt * TILE_M + row;
-      for (int cc = 0; cc < N; cc += 16) {
+      if (ep_src) {
+        // stage the ReLU-mask source tile with row-contiguous loads (tile2 doubles as its buffer: the
+        // batch-norm-backward product overwrites each element in place)
+        const int tb0 = t0 + mt * TILE_M;
+        for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
+          const int r = idx / nq, q = idx - r * nq;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tb0 + r < len_b)
+            x = __ldg(reinterpret_cast<const float4*>(ep_src + (orow0 + tb0 + r) * p.out_stride + n0 + 4 * q));
+          *reinterpret_cast<float4*>(tile2 + r * LDT + 4 * q) = x;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      for (int cc = chalf * 16; cc < N; cc += 32) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + cc), v);
-        const float* es = (ep_src && t < p.T) ? ep_src + (orow0 + t) * p.out_stride + n0 + cc : nullptr;
+        tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(mt * N + cc), v);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          float4 o2 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + j));
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
           if (ep_src) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), s = x;
-            if (es && t < len_b) {
-              x = __ldg(reinterpret_cast<const float4*>(es + j));
-              s = x;
-              if (ep_scale) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
-                s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
-                s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
-              }
+            const float4 x = *reinterpret_cast<const float4*>(tile2 + row * LDT + cc + j);
+            float4 s = x;
+            if (t >= len_b) s = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (ep_scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
+              s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
+              s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
             }
             o.x = s.x > 0.f ? o.x : 0.f; o.y = s.y > 0.f ? o.y : 0.f;
             o.z = s.z > 0.f ? o.z : 0.f; o.w = s.w > 0.f ? o.w : 0.f;
             if (ep_sums) {
               const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + ep_base + cc + j));
               const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + ep_base + cc + j));
+              float4 o2;
               o2.x = o.x * (x.x - mu.x) * rs.x; o2.y = o.y * (x.y - mu.y) * rs.y;
               o2.z = o.z * (x.z - mu.z) * rs.z; o2.w = o.w * (x.w - mu.w) * rs.w;
+              *reinterpret_cast<float4*>(tile2 + row * LDT + cc + j) = o2;
             }
           }
           *reinterpret_cast<float4*>(tile + row * LDT + cc + j) = o;
-          if (ep_sums) *reinterpret_cast<float4*>(tile2 + row * LDT + cc + j) = o2;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int tbase = t0 + mt * TILE_M;
-      for (int idx = tid; idx < TILE_M * nq; idx += 128) {
+      for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
         const int r = idx / nq, q = idx - r * nq;
         if (tbase + r < p.T)
           *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) =
               *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
       }
       if (out_stats || ep_sums) {
-        // all 128 threads: (row group rg, column c); partial sums meet in shared-memory atomics and
+        // all 256 threads: (row group rg, column c); partial sums meet in shared-memory atomics and
         // are flushed to the global double accumulators ONCE per CTA (same-address fp64 atomics from
         // hundreds of CTAs serialise in L2)
         const int valid = max(0, min(TILE_M, len_b - tbase));
-        const int RG = TILE_M / N;                         // N in {16,32,64,128} -> 8,4,2,1 row groups
+        const int RG = FW_PROD / N;                        // N in {16,32,64,128} -> 16,8,4,2 row groups
         const int c = tid % N, rg = tid / N;
         float s0 = 0.f, s1 = 0.f;
         if (out_stats) {
@@ -338,7 +366,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         atomicAdd(&ctl->colacc[0][c], s0);
         atomicAdd(&ctl->colacc[1][c], s1);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if ((out_stats || ep_sums) && tid < N) {
       double* dst = (out_stats ? out_stats : ep_sums) + 2 * (ep_base + tid);
@@ -346,7 +374,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
       atomicAdd(dst + 1, (double)ctl->colacc[1][tid]);
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == FW_PROD / 32) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, N);
@@ -410,7 +438,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == FW_PROD / 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -758,7 +786,7 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   int mt = p.N >= 128 ? 4 : (p.N >= 64 ? 2 : 1);
   while (mt > 1 && (long long)p.B * p.F_out * cdiv(p.T, mt * TILE_M) * p.n_slices < 2 * 148) mt >>= 1;
   size_t rings = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)NB * 2 * KCH * p.N * 16;
-  const size_t tiles = (size_t)(ep_sums ? 2 : 1) * TILE_M * (p.N + 4) * sizeof(float);   // epilogue staging
+  const size_t tiles = (size_t)(ep_src ? 2 : 1) * TILE_M * (p.N + 4) * sizeof(float);   // epilogue staging
   const size_t pad = tiles > rings ? ((tiles - rings + 127) / 128) * 128 : 0;
   const size_t smem = rings + pad + sizeof(SmemCtl) + 128;
   const int t_super = cdiv(p.T, mt * TILE_M);
@@ -768,7 +796,7 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
 #define PBSED_TC_LAUNCH(MTV)                                                                          \
   e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                 \
-  tapgemm_tc_kernel<MTV><<<grid, 192, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
+  tapgemm_tc_kernel<MTV><<<grid, FW_THREADS, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
                                                   ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
                                                   d->no_input_mask ? nullptr : seq_len, t_super, (int)pad);
   if (mt == 4) { PBSED_TC_LAUNCH(4) } else if (mt == 2) { PBSED_TC_LAUNCH(2) } else { PBSED_TC_LAUNCH(1) }
