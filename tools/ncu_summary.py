@@ -26,7 +26,12 @@ def launches(path):
     for row in csv.DictReader(lines):
         if row.get('Metric Name') != 'gpu__time_duration.sum':
             continue
-        v = float(row['Metric Value'].replace(',', ''))
+        try:
+            v = float(row['Metric Value'].replace(',', ''))
+        except ValueError:
+            continue
+        if v != v:
+            continue
         v = {'ns': v / 1e3, 'us': v, 'ms': v * 1e3}.get(row['Metric Unit'], v)
         name = re.sub(r'\(.*', '', row['Kernel Name'])
         agg[name][0] += 1
