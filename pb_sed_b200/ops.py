@@ -29,6 +29,51 @@ def set_default_precision(p):
     _default_precision = PRECISION[p] if isinstance(p, str) else int(p)
 
 
+# ------------------------------------------------------------------ weight-gradient side stream
+# Weight gradients feed nothing but the optimizer, so (when a consumer that joins the stream is in
+# charge, i.e. train.Adam) they are launched on a side stream: they fill the SMs the latency-bound GRU
+# recurrences leave idle and overlap the data-gradient chain instead of sitting on its critical path.
+_wgrad_stream = None
+_wgrad_stream_enabled = False
+
+
+def enable_wgrad_stream(flag=True):
+    global _wgrad_stream_enabled
+    _wgrad_stream_enabled = bool(flag) and os.environ.get('PBSED_WGRAD_STREAM', '1') != '0'
+
+
+class _WgradStream:
+    """context: fork the side stream off the current one and keep the tensors it reads alive."""
+
+    def __init__(self, *tensors):
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        global _wgrad_stream
+        if not _wgrad_stream_enabled:
+            return self
+        if _wgrad_stream is None:
+            _wgrad_stream = torch.cuda.Stream()
+        _wgrad_stream.wait_stream(torch.cuda.current_stream())
+        for t in self.tensors:
+            t.record_stream(_wgrad_stream)
+        self.ctx = torch.cuda.stream(_wgrad_stream)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_wgrad_stream():
+    """make the current stream wait for every weight gradient launched so far."""
+    if _wgrad_stream is not None:
+        torch.cuda.current_stream().wait_stream(_wgrad_stream)
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -254,7 +299,8 @@ class ConvLayerFn(torch.autograd.Function):
         dW, dW_ret = _grad_target(w_p)
         db, db_ret = _grad_target(b_p)
         if dW is not None:
-            tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq if cfg['norm'] else None, mask_out=False)
+            with _WgradStream(x, dz, scale, shift):
+                tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq if cfg['norm'] else None, mask_out=False)
         dx = dg_ret = dbe_ret = None
         if ctx.needs_input_grad[0]:
             rtaps = [(-df, -dt) for df, dt in cfg['taps']]
@@ -374,14 +420,16 @@ class GruMultiFn(torch.autograd.Function):
             dbih, r2 = _grad_target(p_bih)
             dbhh, r3 = _grad_target(p_bhh)
             dx = None
+            with _WgradStream(x, h, dgis[g], dghs[g]):
+                for d in range(nd):
+                    if dwih is not None:
+                        tapgemm_wgrad(x, dgis[g][d], make_desc(B, 1, 1, T, In, H3, [(0, 0)]), dwih[d],
+                                      dbih[d] if dbih is not None else None, seq=seq, mask_out=True)
+                    if dwhh is not None:
+                        desc = make_desc(B, 1, 1, T, H, H3, [(0, 1 if rev[g * nd + d] else -1)], in_stride=nd * H)
+                        tapgemm_wgrad(None, dghs[g][d], desc, dwhh[d], dbhh[d] if dbhh is not None else None,
+                                      seq=seq, mask_out=True, x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * d * H))
             for d in range(nd):
-                if dwih is not None:
-                    tapgemm_wgrad(x, dgis[g][d], make_desc(B, 1, 1, T, In, H3, [(0, 0)]), dwih[d],
-                                  dbih[d] if dbih is not None else None, seq=seq, mask_out=True)
-                if dwhh is not None:
-                    desc = make_desc(B, 1, 1, T, H, H3, [(0, 1 if rev[g * nd + d] else -1)], in_stride=nd * H)
-                    tapgemm_wgrad(None, dghs[g][d], desc, dwhh[d], dbhh[d] if dbhh is not None else None,
-                                  seq=seq, mask_out=True, x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * d * H))
                 if ctx.needs_input_grad[2 + 5 * g]:
                     ddesc = make_desc(B, 1, 1, T, H3, In, [(0, 0)], transpose_w=True)
                     gx = tapgemm(dgis[g][d], w_ihs[g][d], None, ddesc, seq=None).view(B, T, In)

@@ -85,6 +85,7 @@ class Adam:
         self.lr, self.gradient_clipping = lr, gradient_clipping
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.process_group = process_group
+        ops.enable_wgrad_stream(True)      # this optimizer joins the weight-gradient stream before it reads grads
         if self.distributed:
             self.set_grad_scale(1. / dist.get_world_size(process_group))
 
@@ -100,6 +101,7 @@ class Adam:
         self.arena.grads.zero_()
 
     def allreduce_grads(self):
+        ops.join_wgrad_stream()
         if self.distributed:
             allreduce_flat(self.arena.grads, self.process_group)
 
@@ -110,6 +112,7 @@ class Adam:
 
     def update(self):
         a = self.arena
+        ops.join_wgrad_stream()
         call('pbsed_grad_sumsq', _ptr(a.grads), a.n, _ptr(self.hyper), _ptr(self.sumsq), _stream())
         call('pbsed_adam_step', _ptr(a.params), _ptr(a.grads), _ptr(a.exp_avg), _ptr(a.exp_avg_sq),
              a.n, _ptr(self.hyper), _ptr(self.sumsq), _ptr(self.grad_norm), 1, _stream())
