@@ -188,6 +188,38 @@ class GraphedTrainStep:
             if torch.is_tensor(v):
                 self.static[k].copy_(v, non_blocking=True)
 
+    # ---- double-buffered input pipeline: H2D of batch i+1 overlaps the compute of batch i
+    def prefetch(self, host_batch):
+        """start the host->device copy of the NEXT batch (pinned tensors) on a copy stream."""
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [{k: torch.empty_like(v) for k, v in self.static.items() if torch.is_tensor(v)}
+                           for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_idx = 0
+            for e in self._stage_free:
+                e.record()
+        i = self._stage_idx
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[i])
+            for k, v in host_batch.items():
+                if torch.is_tensor(v):
+                    self._stage[i][k].copy_(v, non_blocking=True)
+            self._stage_ready[i].record()
+        self._pending = i
+        self._stage_idx = i ^ 1
+
+    def step_prefetched(self):
+        """run one step on the batch handed to the last prefetch()."""
+        i = self._pending
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready[i])
+        for k, v in self._stage[i].items():
+            self.static[k].copy_(v, non_blocking=True)          # device-to-device, microseconds
+        self._stage_free[i].record(cur)
+        return self()
+
     def __call__(self, batch=None):
         if batch is not None:
             self.load(batch)
