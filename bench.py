@@ -154,6 +154,8 @@ def tapgemm_flops(args):
 def kernel_breakdown(model, opt, batch, train, _lib):
     """one eager, per-call-timed train step: device time + algorithmic FLOPs per C-ABI entry point."""
     import torch
+    from pb_sed_b200 import ops
+    ops.enable_wgrad_stream(False)          # isolate the per-call timings (no concurrent side-stream kernels)
     sink = []
     _lib.profile_sink = sink
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -161,6 +163,7 @@ def kernel_breakdown(model, opt, batch, train, _lib):
     train.train_step(model, opt, batch)
     t1.record()
     _lib.profile_sink = None
+    ops.enable_wgrad_stream(True)
     torch.cuda.synchronize()
     agg = {}
     detail = []

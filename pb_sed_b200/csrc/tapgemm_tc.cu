@@ -22,6 +22,7 @@
 // Operand layouts are the canonical UMMA K-major SWIZZLE_NONE ("interleave") form:
 //   byte(row r, 16-byte k-chunk c) = c*LBO + (r/8)*SBO + (r%8)*16   with SBO = 128  => row pitch 16.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -127,10 +128,12 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
 // image[slice][tap][kb] = { part hi | part lo } x [k-chunk (4)][n (N)][4 floats]
 __global__ void __launch_bounds__(256)
 wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
-             int ntaps, int Cin, int Cout, int N, float* __restrict__ img) {
+             int ntaps, int Cin, int Cout, int N, float* __restrict__ img, double* __restrict__ rep,
+             int rep_count) {
   const int nkb = Cin / KB, n_slices = Cout / N;
   const long long total = (long long)n_slices * ntaps * nkb * KCH * N * 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rep_count; i += stride) rep[i] = 0.;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int e = (int)(i & 3);
     long long q = i >> 2;
@@ -149,6 +152,17 @@ wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn
   }
 }
 
+// fused column sums are accumulated into STAT_REP replicas (CTAs hash onto them) so that thousands of
+// CTAs do not serialise on the same few fp64 addresses in L2; this folds them into the caller's array
+constexpr int STAT_REP = 32;
+__global__ void stat_fold_kernel(const double* __restrict__ rep, int n, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.;
+  for (int r = 0; r < STAT_REP; ++r) s += rep[(long long)r * n + i];
+  dst[i] += s;
+}
+
 // ------------------------------------------------------------------ main kernel
 struct __align__(16) SmemCtl {
   uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], acc_full;
@@ -156,11 +170,10 @@ struct __align__(16) SmemCtl {
   float colacc[2][NSLICE];      // epilogue column sums of one row tile
 };
 
-constexpr int FW_PROD = 256;              // producer / epilogue threads (warps 0-7); warp 8 = MMA, warp 9 = weights
-constexpr int FW_THREADS = FW_PROD + 64;
-
-template <int MT>
-__global__ void __launch_bounds__(FW_THREADS)
+// FW_PROD producer / epilogue threads (4 or 8 warps), then one MMA warp and one weight-loader warp.
+// 8 warps feed the big tiles faster; 4 keep more CTAs co-resident for the narrow, latency-bound layers.
+template <int MT, int NBUF, int FW_PROD>
+__global__ void __launch_bounds__(FW_PROD + 64, NBUF == 2 ? 2 : (FW_PROD == 128 ? 4 : 1))
 tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const float* __restrict__ img, const float* __restrict__ bias,
@@ -168,7 +181,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
                   const float* __restrict__ ep_scale, const float* __restrict__ ep_shift,
                   double* __restrict__ out_stats, const float* __restrict__ ep_mean,
                   const float* __restrict__ ep_rstd, double* __restrict__ ep_sums,
-                  const int* __restrict__ load_seq_len, int t_super, int ctl_pad) {
+                  const int* __restrict__ load_seq_len, int t_super, int ctl_pad, int stat_n) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int N = p.N;
   constexpr int RMAX = MT * TILE_M + 2 * HALO;         // strip rows
@@ -178,7 +191,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
   const uint32_t B_STAGE = 2 * B_PART;
   uint8_t* a_smem = smem_raw;
   uint8_t* b_smem = smem_raw + NA * A_STAGE;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(b_smem + NB * B_STAGE + ctl_pad);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(b_smem + NBUF * B_STAGE + ctl_pad);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x % p.n_slices, st = blockIdx.x / p.n_slices;
@@ -193,7 +206,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&ctl->a_full[i], FW_PROD); mbar_init(&ctl->a_empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&ctl->b_full[i], 1); mbar_init(&ctl->b_empty[i], 1); }
     mbar_init(&ctl->acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,9 +319,9 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
             x = __ldg(reinterpret_cast<const float4*>(ep_src + (orow0 + tb0 + r) * p.out_stride + n0 + 4 * q));
           *reinterpret_cast<float4*>(tile2 + r * LDT + 4 * q) = x;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
       }
-      for (int cc = chalf * 16; cc < N; cc += 32) {
+      for (int cc = chalf * 16; cc < N; cc += FW_PROD / 8) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(mt * N + cc), v);
 #pragma unroll
@@ -342,7 +355,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           *reinterpret_cast<float4*>(tile + row * LDT + cc + j) = o;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
       const int tbase = t0 + mt * TILE_M;
       for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
         const int r = idx / nq, q = idx - r * nq;
@@ -366,10 +379,12 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         atomicAdd(&ctl->colacc[0][c], s0);
         atomicAdd(&ctl->colacc[1][c], s1);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
     }
     if ((out_stats || ep_sums) && tid < N) {
-      double* dst = (out_stats ? out_stats : ep_sums) + 2 * (ep_base + tid);
+      // out_stats / ep_sums point at the replica area here: [STAT_REP][nstat][2]
+      const int repl = (blockIdx.x + blockIdx.y * 7 + blockIdx.z * 13) % STAT_REP;
+      double* dst = (out_stats ? out_stats : ep_sums) + ((long long)repl * stat_n + ep_base + tid) * 2;
       atomicAdd(dst, (double)ctl->colacc[0][tid]);
       atomicAdd(dst + 1, (double)ctl->colacc[1][tid]);
     }
@@ -389,8 +404,8 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           mbar_wait(&ctl->a_full[slot], (it / NA) & 1);
           const uint32_t a_hi = smem_u32(a_smem + slot * A_STAGE), a_lo = a_hi + A_PART;
           for (int j = 0; j < p.g_n[g]; ++j) {
-            const int bslot = bt % NB;
-            mbar_wait(&ctl->b_full[bslot], (bt / NB) & 1);
+            const int bslot = bt % NBUF;
+            mbar_wait(&ctl->b_full[bslot], (bt / NBUF) & 1);
             tc_fence_after();
             const uint32_t b_hi = smem_u32(b_smem + bslot * B_STAGE), b_lo = b_hi + B_PART;
             const int dt = p.g_dt[g][j];
@@ -426,8 +441,8 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           const int f_src = fo + p.g_df[g];
           if (f_src < 0 || f_src >= p.F_in) continue;
           for (int j = 0; j < p.g_n[g]; ++j) {
-            const int bslot = bt % NB;
-            mbar_wait(&ctl->b_empty[bslot], ((bt / NB) & 1) ^ 1);
+            const int bslot = bt % NBUF;
+            mbar_wait(&ctl->b_empty[bslot], ((bt / NBUF) & 1) ^ 1);
             const long long blob = ((long long)(slice * p.ntaps + p.g_tap[g][j]) * p.nkb + kb) * (long long)(B_STAGE / 4);
             mbar_expect_tx(&ctl->b_full[bslot], B_STAGE);
             bulk_g2s(b_smem + bslot * B_STAGE, img + blob, B_STAGE, &ctl->b_full[bslot]);
@@ -570,7 +585,6 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
           continue;
         }
         const int slot = it % WG_STAGES;
-        mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);
         uint8_t* z_hi = smem_raw + slot * STAGE;
         uint8_t* z_lo = z_hi + Z_PART;
         uint8_t* a_hi = z_lo + Z_PART;
@@ -602,6 +616,8 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
               av[k][i] = __ldg(reinterpret_cast<const float4*>(asrc + (long long)t * p.in_stride));
           }
         }
+        // only the stores are gated by the ring slot: the loads above are already in flight
+        mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);
 #pragma unroll
         for (int k = 0; k < ZT; ++k) {
           const int j = zj0 + k * zjs;
@@ -726,9 +742,13 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
 // per-row-tile "first" flag: the first MMA into EACH accumulator must overwrite.  The loop above
 // sets accumulate = 0 only while `first` (the very first (kb, group, tap) triple), for every mt.
 
+static long long img_bytes(const pbsed_tapgemm_desc* d) {
+  return ((2LL * d->ntaps * (long long)d->Cin * d->Cout * (long long)sizeof(float) + 255) / 256) * 256;
+}
 extern "C" long long pbsed_tapgemm_workspace_bytes(const pbsed_tapgemm_desc* d) {
   if (!d || d->precision == 0) return 0;
-  return 2LL * d->ntaps * (long long)d->Cin * d->Cout * sizeof(float) + 256;
+  const long long nstat = (long long)(d->per_f ? d->F_out : 1) * d->Cout;
+  return img_bytes(d) + (long long)STAT_REP * nstat * 2 * sizeof(double) + 256;
 }
 
 static bool tc_eligible(const pbsed_tapgemm_desc* d) {
@@ -774,18 +794,30 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
     p.g_tap[g][p.g_n[g]] = i; p.g_dt[g][p.g_n[g]] = d->dt[i]; ++p.g_n[g];
   }
   float* img = reinterpret_cast<float*>(workspace);
+  const int stat_n = (d->per_f ? d->F_out : 1) * d->Cout;
+  double* rep = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + img_bytes(d));
+  const bool want_sums = out_stats || ep_sums;
   {
     const long long total = (long long)d->ntaps * d->Cin * d->Cout;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img);
+    wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img,
+                                         rep, want_sums ? STAT_REP * stat_n * 2 : 0);
     int rc = pbsed_after_launch();
     if (rc) return rc;
   }
+  double* user_sums = out_stats ? out_stats : ep_sums;
+  if (out_stats) out_stats = rep;
+  if (ep_sums) ep_sums = rep;
   // row tiles per CTA: big N wants many rows per weight fetch, small N wants co-resident CTAs
   int mt = p.N >= 128 ? 4 : (p.N >= 64 ? 2 : 1);
   while (mt > 1 && (long long)p.B * p.F_out * cdiv(p.T, mt * TILE_M) * p.n_slices < 2 * 148) mt >>= 1;
-  size_t rings = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)NB * 2 * KCH * p.N * 16;
+  // N = 128: two co-resident CTAs per SM (2 row tiles, 2 weight stages each, 2 x 256 TMEM columns) so that
+  // one CTA's prologue / epilogue overlaps the other's MMAs
+  static const int two_cta = getenv("PBSED_TC_2CTA") ? atoi(getenv("PBSED_TC_2CTA")) : 1;
+  int nbuf = NB;
+  if (two_cta && p.N == 128 && mt >= 2 && (long long)p.B * p.F_out * cdiv(p.T, 2 * TILE_M) * p.n_slices >= 2 * 148) { mt = 2; nbuf = 2; }
+  size_t rings = (size_t)NA * 2 * KCH * (mt * TILE_M + 2 * HALO) * 16 + (size_t)nbuf * 2 * KCH * p.N * 16;
   const size_t tiles = (size_t)(ep_src ? 2 : 1) * TILE_M * (p.N + 4) * sizeof(float);   // epilogue staging
   const size_t pad = tiles > rings ? ((tiles - rings + 127) / 128) * 128 : 0;
   const size_t smem = rings + pad + sizeof(SmemCtl) + 128;
@@ -793,15 +825,19 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   dim3 grid(t_super * p.n_slices, p.F_out, p.B);
   if (grid.y > 65535 || grid.z > 65535) return 0;
   cudaError_t e;
-#define PBSED_TC_LAUNCH(MTV)                                                                          \
-  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+#define PBSED_TC_LAUNCH(MTV, NBV, PRV)                                                                \
+  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV, NBV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                 \
-  tapgemm_tc_kernel<MTV><<<grid, FW_THREADS, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
+  tapgemm_tc_kernel<MTV, NBV, PRV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
                                                   ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
-                                                  d->no_input_mask ? nullptr : seq_len, t_super, (int)pad);
-  if (mt == 4) { PBSED_TC_LAUNCH(4) } else if (mt == 2) { PBSED_TC_LAUNCH(2) } else { PBSED_TC_LAUNCH(1) }
+                                                  d->no_input_mask ? nullptr : seq_len, t_super, (int)pad, stat_n);
+  if (nbuf == 2) { PBSED_TC_LAUNCH(2, 2, 256) } else if (mt == 4) { PBSED_TC_LAUNCH(4, 4, 256) } else if (mt == 2) { PBSED_TC_LAUNCH(2, 4, 256) }
+  else if (p.N <= 32) { PBSED_TC_LAUNCH(1, 4, 128) } else { PBSED_TC_LAUNCH(1, 4, 256) }
 #undef PBSED_TC_LAUNCH
   *handled = 1;
+  int rc = pbsed_after_launch();
+  if (rc || !want_sums) return rc;
+  stat_fold_kernel<<<cdiv(2 * stat_n, 256), 256, 0, st>>>(rep, 2 * stat_n, user_sums);
   return pbsed_after_launch();
 }
 
