@@ -211,7 +211,7 @@ def run_gpu(args):
     torch.manual_seed(0)
     model = weak_label.CRNN.from_config_dict(config.fbcrnn_config(num_events=NUM_EVENTS)).to(dev)
     model.emit_buffers = False
-    opt = train.Adam(model, lr=5e-4, gradient_clipping=1e10)
+    opt = train.Adam(model, lr=5e-4, gradient_clipping=1e10, sync_stats=args.sync_stats)
 
     n_sets = 3
     host = []
@@ -286,6 +286,7 @@ def run_gpu(args):
                                    '16 kHz clips, K=10, fp32, full train step (GPU STFT+logmel, CNN, fwd+bwd GRU, '
                                    'pb_sed loss, backward, clip+Adam)',
                        'global_batch': B * world, 'parallelism': f'dp{world}', 'precision': args.precision,
+                       'sync_stats': args.sync_stats if world > 1 else 'n/a (1 GPU)',
                        'l2': f'{n_sets} distinct input batches rotate; per-step activation working set (several GB) '
                              '>> 126 MB L2', 'cuda_graph': True, 'final_loss': final_loss},
             'e2e': {'value': e2e, 'unit': '10s-clips/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
@@ -322,6 +323,7 @@ def run_gpu(args):
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
+        step.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -335,6 +337,8 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sync-stats', default='none', choices=['none', 'exact'],
+                    help="N > 1: per-replica batch statistics ('none') or all-reduced ('exact', SURVEY 8e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

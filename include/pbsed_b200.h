@@ -143,7 +143,10 @@ int pbsed_channel_stats(const float* x, int B, int F, int T, int C, int per_f,
  *   momentum <  0: cumulative average over num_tracked (feature-extractor norm)
  *   training == 0: scale/shift from running statistics, nothing updated.
  *   cumulative (momentum<0) & training: scale/shift from the UPDATED running stats
- *   (interpolation_factor = 1), var unbiased n/(n-1) as padertorch does for momentum None. */
+ *   (interpolation_factor = 1), var unbiased n/(n-1) as padertorch does for momentum None.
+ *   count <= 0 (training): the count is read on the device from stats[2*nch] -- the data-parallel
+ *   "exact" mode all-reduces (sum, sum of squares, count) of every replica in one buffer
+ *    and never brings the global count back to the host. */
 int pbsed_norm_finalize(const double* stats, double count, int nch,
                         const float* gamma, const float* beta, float eps, float momentum, int training,
                         float* running_mean, float* running_power, float* num_tracked,
@@ -157,7 +160,9 @@ int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T
  * multiplied by the ReLU mask), x = the layer input the statistics were taken on.
  *   pass 1: sums[idx][0] += sum g ; sums[idx][1] += sum g * xhat       (valid rows only)
  *   pass 2: dx = gamma*rstd * ( g - sums0/n - xhat * sums1/n ) ; dgamma += sums1 ; dbeta += sums0
- *           rows t >= seq_len[b] get dx = 0.  dx may alias g. */
+ *           rows t >= seq_len[b] get dx = 0.  dx may alias g.
+ *           count <= 0: n is read on the device from sums[2*nch] (see pbsed_norm_finalize);
+ *           dgamma / dbeta nullable (data-parallel: the replica adds its LOCAL sums itself). */
 int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int F, int T, int C, int per_f,
                           const int* seq_len, const float* save_mean, const float* save_rstd,
                           double* sums, void* stream);

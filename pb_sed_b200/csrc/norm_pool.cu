@@ -182,6 +182,7 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, double co
                                      float* __restrict__ save_rstd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nch) return;
+  if (training && count <= 0.) count = stats[2 * nch];     // device-side count (data-parallel exact statistics)
   const float ga = gamma ? gamma[i] : 1.f;
   const float be = beta ? beta[i] : 0.f;
   float mu, var;
@@ -227,7 +228,7 @@ extern "C" int pbsed_norm_finalize(const double* stats, double count, int nch, c
                                    float* scale, float* shift, float* save_mean, float* save_rstd,
                                    void* stream) {
   if (nch < 1 || !scale || !shift) return PBSED_EINVAL;
-  if (training && (!stats || count <= 0.)) return PBSED_EINVAL;
+  if (training && !stats) return PBSED_EINVAL;
   if (!training && (!running_mean || !running_power)) return PBSED_EINVAL;
   if (running_mean && (!running_power || !num_tracked)) return PBSED_EINVAL;
   norm_finalize_kernel<<<cdiv(nch, 128), 128, 0, (cudaStream_t)stream>>>(
@@ -244,6 +245,7 @@ norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, 
                       const double* __restrict__ sums, float inv_n, float* __restrict__ dx,
                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total,
                       int nch) {
+  if (inv_n <= 0.f) inv_n = (float)(1.0 / sums[2 * nch]);   // device-side count
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c = (int)(i % C);
@@ -277,6 +279,7 @@ norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ 
                        const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                        const double* __restrict__ sums, float inv_n, float4* __restrict__ dx,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch) {
+  if (inv_n <= 0.f) inv_n = (float)(1.0 / sums[2 * nch]);   // device-side count
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     const int q = (int)(i % C4);
@@ -311,8 +314,9 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
                                     const float* save_rstd, const float* gamma, const double* sums,
                                     double count, float* dx, float* dgamma, float* dbeta,
                                     void* stream) {
-  if (!g || !x || !sums || !dx || !save_mean || !save_rstd || count <= 0.) return PBSED_EINVAL;
+  if (!g || !x || !sums || !dx || !save_mean || !save_rstd) return PBSED_EINVAL;
   if ((dgamma == nullptr) != (dbeta == nullptr)) return PBSED_EINVAL;
+  const float inv_count = count > 0. ? (float)(1.0 / count) : 0.f;   // <= 0: count = sums[2*nch] on the device
   const long long total = (long long)B * F * T * C;
   const int nch = per_f ? F * C : C;
   if ((C & 3) == 0 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
@@ -323,14 +327,14 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
     norm_bwd_apply4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x), F, T, C / 4, per_f, seq_len,
         reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
-        reinterpret_cast<const float4*>(gamma), sums, (float)(1.0 / count), reinterpret_cast<float4*>(dx),
+        reinterpret_cast<const float4*>(gamma), sums, inv_count, reinterpret_cast<float4*>(dx),
         dgamma, dbeta, total4, nch);
     return pbsed_after_launch();
   }
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   norm_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      g, x, F, T, C, per_f, seq_len, save_mean, save_rstd, gamma, sums, (float)(1.0 / count), dx,
+      g, x, F, T, C, per_f, seq_len, save_mean, save_rstd, gamma, sums, inv_count, dx,
       dgamma, dbeta, total, nch);
   return pbsed_after_launch();
 }

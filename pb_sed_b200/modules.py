@@ -607,7 +607,7 @@ class NormalizedLogMelExtractor(nn.Module):
                 B, C, T = x.shape[:3]
                 assert C == 1
                 seq = SeqLen.make(seq_len, B, T, x.device)
-                stats = torch.zeros((self.number_of_filters, 2), device=x.device, dtype=torch.float64) if train else None
+                stats = ops._stats_buffer(self.number_of_filters, x.device) if train else None
                 y = ops.logmel_from_stft(x.reshape(B, T, x.shape[3], 2), self._fb(), seq, stats)
             else:
                 a = x.reshape(x.shape[0], -1)
@@ -617,11 +617,12 @@ class NormalizedLogMelExtractor(nn.Module):
                 pad_front = {'half': (kw['window_length'] - kw['shift']) // 2, 'full': kw['window_length'] - kw['shift'],
                              True: kw['window_length'] - kw['shift']}.get(kw['fading'], 0)
                 seq = SeqLen.make(seq_len, B, T, x.device)
-                stats = torch.zeros((self.number_of_filters, 2), device=x.device, dtype=torch.float64) if train else None
+                stats = ops._stats_buffer(self.number_of_filters, x.device) if train else None
                 cfg = dict(shift=kw['shift'], window_length=kw['window_length'], size=kw['size'],
                            pad_front=pad_front, T=T, window=self._window)
                 y = ops.logmel_from_audio(a, cfg, self._fb(), seq, stats)
-            scale, shift = ops.norm_finalize(stats, seq.frames() if train else 1., self.number_of_filters,
+            count = ops._sync_count_(stats, self.number_of_filters, seq.frames()) if train else 1.
+            scale, shift = ops.norm_finalize(stats, count, self.number_of_filters,
                                              None, None, n.eps, -1., train, n.running_mean,
                                              n.running_power, n.num_tracked_values, x.device)
             ops.logmel_normalize_(y, scale, shift, self.clamp, seq)

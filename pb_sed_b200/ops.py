@@ -74,6 +74,50 @@ def join_wgrad_stream():
         torch.cuda.current_stream().wait_stream(_wgrad_stream)
 
 
+# ------------------------------------------------------------------ data-parallel exact statistics
+# clips shard over ranks, but the 15 batch-norm layers (and the feature extractor's running
+# normalisation, and the loss normaliser) reduce over the WHOLE batch in the single-process reference.
+# 'exact' all-reduces (sum, sum of squares, count) per norm layer -- one small buffer, the count rides
+# in its last row and stays on the device -- in forward, the mirrored (sum g, sum g*xhat, count) in
+# backward, and (loss numerator, sum of weights) in the loss, so that N replicas reproduce the
+# single-process step.  'none' keeps per-replica statistics (what DistributedDataParallel would do).
+_sync = {'on': False, 'group': None}
+
+
+def set_sync_stats(mode='none', group=None):
+    assert mode in ('none', 'exact'), mode
+    import torch.distributed as dist
+    on = mode == 'exact' and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    _sync['on'], _sync['group'] = on, group
+
+
+def sync_stats_on():
+    return _sync['on']
+
+
+def allreduce_stats_(t):
+    """in-place sum over the replicas of a small statistics buffer (NCCL on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+    if _sync['on']:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_sync['group'])
+    return t
+
+
+def _stats_buffer(nch, device):
+    """(nch [+1], 2) float64 zeros; the extra row carries the replica's count in 'exact' mode."""
+    return torch.zeros((nch + (1 if _sync['on'] else 0), 2), device=device, dtype=torch.float64)
+
+
+def _sync_count_(stats, nch, count):
+    """'exact': put the local count in the last row, all-reduce, and tell the kernel (count = 0) to read
+    the global count from the buffer.  Otherwise return the host count unchanged."""
+    if not _sync['on']:
+        return float(count)
+    stats[nch:nch + 1, 0:1].fill_(float(count))       # fill kernel: no H2D copy, graph-capturable
+    allreduce_stats_(stats)
+    return 0.0
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -233,15 +277,15 @@ class ConvLayerFn(torch.autograd.Function):
             scale = torch.empty(nch, device=x.device)
             shift = torch.empty(nch, device=x.device)
             if cfg['training']:
-                if stats_in is not None and stats_in.numel() == 2 * nch:
+                if stats_in is not None and stats_in.shape[0] == nch + (1 if _sync['on'] else 0):
                     stats = stats_in
                 else:
-                    stats = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
+                    stats = _stats_buffer(nch, x.device)
                     call('pbsed_channel_stats', _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
                          _ptr(stats), _stream())
                 smean = torch.empty(nch, device=x.device)
                 srstd = torch.empty(nch, device=x.device)
-                call('pbsed_norm_finalize', _ptr(stats), count, nch, _ptr(gamma), _ptr(beta),
+                call('pbsed_norm_finalize', _ptr(stats), _sync_count_(stats, nch, count), nch, _ptr(gamma), _ptr(beta),
                      cfg['eps'], cfg['momentum'], 1, _ptr(rmean), _ptr(rpower), _ptr(ntracked),
                      _ptr(scale), _ptr(shift), _ptr(smean), _ptr(srstd), _stream())
             else:
@@ -257,7 +301,7 @@ class ConvLayerFn(torch.autograd.Function):
             sp = cfg.get('stats_per_f', False)
             desc_s = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
                                no_input_mask=not cfg['norm'])
-            stats_out = torch.zeros(((F_out if sp else 1) * Cout, 2), device=x.device, dtype=torch.float64)
+            stats_out = _stats_buffer((F_out if sp else 1) * Cout, x.device)
             if sp == per_f:
                 z = tapgemm(x, weight, bias, desc_s, scale, shift, seq, out_stats=stats_out)
             else:      # statistics indexed differently from the load affine: separate pass
@@ -310,7 +354,7 @@ class ConvLayerFn(torch.autograd.Function):
             fuse = train_norm and cfg['relu']          # batch-norm backward pass 1 rides in the dgrad epilogue
             if train_norm:
                 nch = (F_in if per_f else 1) * Cin
-                sums = torch.zeros((nch, 2), device=x.device, dtype=torch.float64)
+                sums = _stats_buffer(nch, x.device)
             g = tapgemm(dz, weight, None, ddesc, None, None, seq,
                         ep_src=x if cfg['relu'] else None,
                         ep_scale=scale if cfg['relu'] else None,
@@ -323,9 +367,20 @@ class ConvLayerFn(torch.autograd.Function):
                          _ptr(smean), _ptr(srstd), _ptr(sums), _stream())
                 dga, dg_ret = _grad_target(g_p)
                 dbe, dbe_ret = _grad_target(be_p)
-                call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                     _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), ctx.count, _ptr(g),
-                     _ptr(dga), _ptr(dbe), _stream())
+                if _sync['on']:
+                    # dx needs the sums over ALL replicas; dgamma / dbeta take the local ones (the flat
+                    # gradient all-reduce adds the other replicas' later)
+                    local = sums[:nch].float()
+                    cnt = _sync_count_(sums, nch, ctx.count)
+                    call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                         _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), cnt, _ptr(g), None, None, _stream())
+                    if dga is not None:
+                        dga.add_(local[:, 1])
+                        dbe.add_(local[:, 0])
+                else:
+                    call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
+                         _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), ctx.count, _ptr(g),
+                         _ptr(dga), _ptr(dbe), _stream())
                 dx = g
             elif cfg['norm']:
                 # eval-mode norm is a fixed affine: dx = g * scale  (rare: frozen-stat finetuning)
@@ -485,6 +540,19 @@ class SigmoidScoresFn(torch.autograd.Function):
         return dz, None
 
 
+def _sync_loss(out):
+    """out = (local loss = N_r / D_r, D_r = local sum of weights).  'exact' data parallelism: the
+    single-process loss is sum_r N_r / sum_r D_r, so the replica's gradient is rescaled by
+    D_r * world / D_global (the flat all-reduce + 1/world then yields the exact gradient)."""
+    if not _sync['on']:
+        return out[0], torch.ones((), device=out.device)
+    import torch.distributed as dist
+    world = dist.get_world_size(_sync['group'])
+    packed = torch.stack([out[0] * out[1], out[1]])
+    allreduce_stats_(packed)
+    return packed[0] / packed[1], out[1] * world / packed[1]
+
+
 class FbcrnnLossFn(torch.autograd.Function):
     """pb_sed weak_label CRNN.review loss (weak_label/crnn.py:117-153); value and gradient
     come out of the same kernel pass."""
@@ -504,12 +572,14 @@ class FbcrnnLossFn(torch.autograd.Function):
         call('pbsed_fbcrnn_loss', _ptr(y_fwd), _ptr(y_bwd), _ptr(weak), _ptr(boundary), _ptr(cw),
              seq.ptr, B, K, T, float(strong_weight), float(smoothing), _ptr(out), _ptr(dyf),
              _ptr(dyb), _ptr(ws), _stream())
-        ctx.save_for_backward(dyf, dyb)
-        return out[0]
+        loss, gscale = _sync_loss(out)
+        ctx.save_for_backward(dyf, dyb, gscale)
+        return loss
 
     @staticmethod
     def backward(ctx, dl):
-        dyf, dyb = ctx.saved_tensors
+        dyf, dyb, gscale = ctx.saved_tensors
+        dl = dl * gscale
         return (dyf * dl, None if dyb is None else dyb * dl, None, None, None, None, None, None)
 
 
@@ -526,13 +596,14 @@ class BicrnnLossFn(torch.autograd.Function):
         dy = torch.empty_like(y)
         call('pbsed_bicrnn_loss', _ptr(y), _ptr(strong), seq.ptr, B, K, T, _ptr(out), _ptr(dy),
              _ptr(ws), _stream())
-        ctx.save_for_backward(dy)
-        return out[0]
+        loss, gscale = _sync_loss(out)
+        ctx.save_for_backward(dy, gscale)
+        return loss
 
     @staticmethod
     def backward(ctx, dl):
-        dy, = ctx.saved_tensors
-        return dy * dl, None, None
+        dy, gscale = ctx.saved_tensors
+        return dy * (dl * gscale), None, None
 
 
 # ------------------------------------------------------------------ features

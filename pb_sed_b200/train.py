@@ -75,7 +75,10 @@ class Adam:
     """padertorch.train.optimizer.Adam surface over the fused kernel (betas/eps = torch defaults)."""
 
     def __init__(self, model, lr=5e-4, gradient_clipping=1e10, betas=(0.9, 0.999), eps=1e-8,
-                 process_group=None, distributed=None):
+                 process_group=None, distributed=None, sync_stats='none'):
+        """sync_stats (data parallel only): 'none' = per-replica batch statistics; 'exact' = every
+        batch-norm / running-norm / loss normaliser reduces over all replicas (``ops.set_sync_stats``),
+        so that N replicas reproduce the single-process step on the concatenated batch."""
         self.arena = FlatArena(model)
         dev = self.arena.params.device
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, gradient_clipping, 0., 1., 0.],
@@ -88,6 +91,8 @@ class Adam:
         ops.enable_wgrad_stream(True)      # this optimizer joins the weight-gradient stream before it reads grads
         if self.distributed:
             self.set_grad_scale(1. / dist.get_world_size(process_group))
+        self.sync_stats = sync_stats
+        ops.set_sync_stats(sync_stats if self.distributed else 'none', process_group)
 
     def set_lr(self, lr):
         """LRAnnealingHook equivalent: the LR is a device scalar, valid under graph replay."""
@@ -110,9 +115,10 @@ class Adam:
         self.allreduce_grads()
         return self.update()
 
-    def update(self):
+    def update(self, join=True):
         a = self.arena
-        ops.join_wgrad_stream()
+        if join:
+            ops.join_wgrad_stream()
         call('pbsed_grad_sumsq', _ptr(a.grads), a.n, _ptr(self.hyper), _ptr(self.sumsq), _stream())
         call('pbsed_adam_step', _ptr(a.params), _ptr(a.grads), _ptr(a.exp_avg), _ptr(a.exp_avg_sq),
              a.n, _ptr(self.hyper), _ptr(self.sumsq), _ptr(self.grad_norm), 1, _stream())
@@ -164,10 +170,12 @@ class GraphedTrainStep:
             self.loss = self._fwd_bwd()
             if not self.split:
                 self.grad_norm = self.optimizer.update()
+            else:
+                ops.join_wgrad_stream()       # a capture must end with every forked stream joined
         if self.split:
             self.graph_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_update):
-                self.grad_norm = self.optimizer.update()
+                self.grad_norm = self.optimizer.update(join=False)     # joined at the end of the first graph
         self.optimizer.arena.rebind_grads()
 
     def _fwd_bwd(self):
@@ -182,6 +190,16 @@ class GraphedTrainStep:
     def _body(self):
         loss = self._fwd_bwd()
         return loss, self.optimizer.step()
+
+    def close(self):
+        """release the captured graphs (do this before tearing down a process group whose collectives
+        were captured: 'exact' statistics put NCCL kernels inside the forward/backward graph)."""
+        torch.cuda.synchronize()
+        for name in ('graph', 'graph_update'):
+            g = getattr(self, name, None)
+            if g is not None:
+                g.reset()
+                setattr(self, name, None)
 
     def load(self, batch):
         for k, v in batch.items():
