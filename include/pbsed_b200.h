@@ -242,6 +242,28 @@ int pbsed_grad_sumsq(const float* g, long long n, const float* hyper, double* su
 int pbsed_adam_step(float* p, float* g, float* m, float* v, long long n, float* hyper,
                     double* sumsq, float* grad_norm_out, int zero_grad, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * K6  score post-processing of the inference path (the reference does this in
+ *     numpy after a D2H copy: pb_sed/models/base/inference.py:143-183,225-289, pb_sed/filters.py)
+ *
+ * Scores (B, [N,] K, T) are addressed as R rows of T frames.  filt_len (device int32[filt_mod]):
+ * the filter length of row r is filt_len[r % filt_mod] (1 = scalar, K = per class, N*K = per
+ * (n, class): the three cases of inference.py:225-266).  seq_len (nullable, device int32[B]):
+ * clip b = r / rows_per_clip; frames t >= seq_len[b] are read as 0 (inference.py:143-147).
+ */
+/* y[r,t] = median of x[r, t-h .. t+h], zeros outside [0,T), h = (n-1)/2, n odd (n <= 1: copy);
+ * = scipy.signal.medfilt per row (pb_sed/filters.py:56-83).  Selection: bit-exact. */
+int pbsed_medfilt(const float* x, int R, int T, const int* filt_len, int filt_mod,
+                  const int* seq_len, int rows_per_clip, float* y, void* stream);
+/* boundariesfilt (inference.py:269-289): s = stepfilt(x, n) (filters.py:113-135; n even, n = 0: s = x),
+ * y = min( cummax_t(s_fwd), flip(cummax(s of the flipped row)) ), computed and returned in float64
+ * like the reference (np.correlate with a float64 kernel). */
+int pbsed_boundariesfilt(const float* x, int R, int T, const int* filt_len, int filt_mod,
+                         const int* seq_len, int rows_per_clip, double* y, void* stream);
+/* scores (B,N,K,T) *= max(tags[b,k], 1 - apply[n,k])   (inference.py:170-183; tags (B,K), apply (N,K)) */
+int pbsed_tag_mask(float* scores, const float* tags, const float* apply, int B, int N, int K, int T,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

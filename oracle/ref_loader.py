@@ -100,3 +100,32 @@ def load():
     strong = _exec('pb_sed.models.strong_label.crnn', 'pb_sed/models/strong_label/crnn.py')
     _loaded.update(weak=weak, strong=strong)
     return weak, strong
+
+
+def load_filters():
+    """the REAL ``pb_sed/filters.py`` and the post-processing functions of
+    ``pb_sed/models/base/inference.py`` (``filtering``, ``boundariesfilt``), executed unmodified;
+    everything they import that is absent here (sed_scores_eval, padertorch, paderbox) is stubbed --
+    the functions used run on numpy / scipy / torch only."""
+    if 'filters' in _loaded:
+        return _loaded['filters'], _loaded['inference']
+    assert reference_available(), REFERENCE_ROOT
+    if not hasattr(np, 'int'):
+        np.int = int
+    if not hasattr(np, 'bool'):
+        np.bool = bool
+    for name in ('paderbox', 'paderbox.array', 'pb_sed', 'pb_sed.utils', 'sed_scores_eval',
+                 'sed_scores_eval.utils', 'padertorch', 'padertorch.ops', 'padertorch.ops.sequence'):
+        if name not in sys.modules:
+            _stub(name)
+    _stub('paderbox.array.segment', segment_axis=segment_axis)
+    _stub('pb_sed.utils.segment', segment_batch=None, merge_segments=None)
+    _stub('sed_scores_eval.utils.scores', create_score_dataframe=None)
+    sys.modules['sed_scores_eval'].io = None
+    if 'padertorch.ops.sequence.mask' not in sys.modules:
+        _stub('padertorch.ops.sequence.mask', compute_mask=pt_port.compute_mask)
+    filt = _exec('pb_sed.filters', 'pb_sed/filters.py')
+    sys.modules['pb_sed'].filters = filt
+    inf = _exec('pb_sed.models.base.inference', 'pb_sed/models/base/inference.py')
+    _loaded.update(filters=filt, inference=inf)
+    return filt, inf

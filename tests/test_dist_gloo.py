@@ -60,3 +60,49 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _sync_worker(rank, world, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pb_sed_b200 import ops, train
+    ops.set_sync_stats('exact')
+    assert ops.sync_stats_on()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 3, 7, 4, generator=g, dtype=torch.float64)        # (B, F, T, C) rows x channels
+    lens = [7, 7, 5, 4, 3, 2]
+    lo, hi = train.shard_bounds(6, rank, world)
+    nch = 4
+    stats = ops._stats_buffer(nch, 'cpu')
+    assert stats.shape == (nch + 1, 2)
+    count = 0.
+    for b in range(lo, hi):
+        v = x[b, :, :lens[b]].reshape(-1, nch)
+        stats[:nch, 0] += v.sum(0)
+        stats[:nch, 1] += (v * v).sum(0)
+        count += v.shape[0]
+    assert ops._sync_count_(stats, nch, count) == 0.0                      # kernel reads the count on device
+    # loss: replica value N_r / D_r with D_r weights -> global loss and the replica's gradient scale
+    N, D = [3.0, 1.0][rank], [4.0, 1.0][rank]
+    loss, gscale = ops._sync_loss(torch.tensor([N / D, D], dtype=torch.float64))
+    torch.save({'stats': stats, 'loss': loss, 'gscale': gscale}, os.path.join(out_dir, f's{rank}.pt'))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exact_statistics_allreduce_world2(tmp_path):
+    """SURVEY 8e 'exact' mode host logic: (sum, sum of squares, count) of every replica in one buffer;
+    loss numerator / normaliser all-reduced, gradient scale D_r * world / D_global."""
+    world = 2
+    mp.spawn(_sync_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(tmp_path / f's{i}.pt') for i in range(world)]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 3, 7, 4, generator=g, dtype=torch.float64)
+    lens = [7, 7, 5, 4, 3, 2]
+    rows = torch.cat([x[b, :, :lens[b]].reshape(-1, 4) for b in range(6)])
+    for s in r:
+        assert torch.allclose(s['stats'][:4, 0], rows.sum(0)) and torch.allclose(s['stats'][:4, 1], (rows * rows).sum(0))
+        assert float(s['stats'][4, 0]) == rows.shape[0]
+        assert abs(float(s['loss']) - (3.0 + 1.0) / (4.0 + 1.0)) < 1e-12
+    assert abs(float(r[0]['gscale']) - 4.0 * 2 / 5.0) < 1e-12 and abs(float(r[1]['gscale']) - 1.0 * 2 / 5.0) < 1e-12
