@@ -49,26 +49,48 @@ long long pbsed_launch_count(void);
  * for bins lo..hi-1 (row-normalised HTK-mel triangles).
  * stats (nullable): double[n_mels][2], accumulates sum / sum-of-squares of logmel
  * over valid frames (t < seq_len[b]) for the cumulative running normalisation.
+ * fbank_per_clip != 0: every clip has its own filterbank (train-time MelWarping,
+ * training.py:195-208): fbank_lo/hi are (B, n_mels), fbank_w is (B, n_mels, fbank_stride).
+ * frame_start (nullable, int32 (B, T)): first sample of every frame in the 'fading'-padded
+ * signal instead of t*shift -- the non-uniform frame grid of TimeWarpedSTFT
+ * (pb_sed/data_preparation/transform.py:36-45, samplers provider.py:329-338).
  */
 int pbsed_stft_logmel(const float* audio, int B, int S,
                       int shift, int window_length, int fft_size, int pad_front, int T,
                       const float* window,
                       const int* fbank_lo, const int* fbank_hi, const float* fbank_w,
-                      int fbank_stride, int n_mels,
+                      int fbank_stride, int n_mels, int fbank_per_clip, const int* frame_start,
                       const int* seq_len, float* logmel, double* stats, void* stream);
 
 /* power spectrogram input variant (reference-compatible 5-D `stft` input,
  * (B, T, n_bins, 2) fp32 re/im):  same outputs as above. */
 int pbsed_spec_logmel(const float* stft, int B, int T, int n_bins,
                       const int* fbank_lo, const int* fbank_hi, const float* fbank_w,
-                      int fbank_stride, int n_mels,
+                      int fbank_stride, int n_mels, int fbank_per_clip,
                       const int* seq_len, float* logmel, double* stats, void* stream);
+
+/* per-example warped HTK-mel filterbanks (paderbox MelWarping as configured at
+ * pb_sed/experiments/weak_label_crnn/training.py:195-208; piecewise-linear warp of the filter edge
+ * frequencies in the mel domain, see stft_logmel.cu).  alpha / ratio: device float[B] (warp factor,
+ * boundary-frequency ratio).  mel_lo / mel_hi: mel of the lowest / highest filter edge, mel_warp_hi:
+ * mel of MelWarping.highest_frequency, bins_per_hz = fft_size / sample_rate.  Writes the sparse
+ * tables pbsed_stft_logmel reads with fbank_per_clip = 1. */
+int pbsed_make_warped_fbank(const float* alpha, const float* ratio, int B, int n_mels, int n_bins,
+                            double mel_lo, double mel_hi, double mel_warp_hi, double bins_per_hz,
+                            int* fbank_lo, int* fbank_hi, float* fbank_w, int fbank_stride,
+                            void* stream);
 
 /* normalise + clamp + mask in place:  x = clamp(x * scale[f] + shift[f], +-clamp) * (t < seq_len[b])
  * with scale = rsqrt(var+eps), shift = -mean*scale from pbsed_norm_finalize
  * (padertorch Normalization('bcft', statistics_axis='bt', no affine) + clamp(+-6)) */
+/* train-time augmentation fused into the same pass (all nullable / 0; kwargs at
+ * training.py:210-216): time_masks int32 (B, n_time_masks, 2) = (onset frame, width),
+ * freq_masks int32 (B, n_freq_masks, 2) = (onset band, width) -> zeroed after the clamp;
+ * then x += noise_scale[b] * noise (noise (B,F,T) standard normal). */
 int pbsed_logmel_normalize(float* x, int B, int F, int T, const float* scale, const float* shift,
-                           float clamp, const int* seq_len, void* stream);
+                           float clamp, const int* seq_len,
+                           const int* time_masks, int n_time_masks, const int* freq_masks, int n_freq_masks,
+                           const float* noise, const float* noise_scale, void* stream);
 
 /* ---------------------------------------------------------------------------
  * K2  tap-GEMM: the one contraction behind CNN2d / CNN1d / GRU projections / output_net

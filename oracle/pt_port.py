@@ -40,8 +40,11 @@ def stft_frames(num_samples, shift=320, window_length=960, fading='half', pad=Tr
     return (num_samples - window_length) // shift + 1
 
 
-def stft(audio, shift=320, window_length=960, size=1024, fading='half', pad=True):
+def stft(audio, shift=320, window_length=960, size=1024, fading='half', pad=True, frame_start=None):
     """audio (..., S) -> complex (..., T, size//2+1), float64 math.
+
+    frame_start (B, T) int: TimeWarpedSTFT [R] -- first sample of every frame in the faded signal
+    instead of t*shift (audio must then be (B, S) or (B, 1, S)).
 
     [R] fading='half' zero-pads (window_length-shift)//2 in front and
     ceil((window_length-shift)/2) at the end; pad=True keeps the last partial
@@ -64,9 +67,32 @@ def stft(audio, shift=320, window_length=960, size=1024, fading='half', pad=True
         need = (t - 1) * shift + window_length
         if need > n:
             audio = np.pad(audio, [(0, 0)] * (audio.ndim - 1) + [(0, need - n)])
+    if frame_start is not None:
+        fs = np.asarray(frame_start)
+        assert fs.shape[-1] == t, (fs.shape, t)
+        idx = fs[..., None] + np.arange(window_length)                  # (B, T, W)
+        flat = audio.reshape(fs.shape[0], -1)
+        flat = np.pad(flat, [(0, 0), (0, max(int(idx.max()) + 1 - flat.shape[-1], 0))])
+        frames = np.take_along_axis(flat[:, None, :], idx.reshape(fs.shape[0], 1, -1), axis=-1)
+        frames = frames.reshape(fs.shape[0], t, window_length) * blackman_periodic(window_length)
+        return np.fft.rfft(frames, n=size, axis=-1).reshape(audio.shape[:-1] + (t, size // 2 + 1))
     idx = np.arange(t)[:, None] * shift + np.arange(window_length)[None, :]
     frames = audio[..., idx] * blackman_periodic(window_length)
     return np.fft.rfft(frames, n=size, axis=-1)
+
+
+def time_warp_grid(anchor, anchor_shift, num_frames, shift):
+    """TimeWarpedSTFT [R] (transform.py:36-45; samplers provider.py:329-338: anchor ~ U(.4,.6),
+    anchor_shift ~ U(-.1,.1), both relative to the clip length): output frame t reads the source
+    position src(t) (in frames), piecewise linear with src(0)=0, src((anchor+anchor_shift) T) = anchor T,
+    src(T) = T.  Returns (src (B,T) float64, frame_start (B,T) int = round(src * shift))."""
+    a_in = np.asarray(anchor, dtype=np.float64)[:, None] * num_frames
+    a_out = np.clip((np.asarray(anchor, dtype=np.float64) + np.asarray(anchor_shift, dtype=np.float64))[:, None]
+                    * num_frames, 1., num_frames - 1.)
+    t = np.arange(num_frames, dtype=np.float64)[None]
+    src = np.where(t <= a_out, t * a_in / a_out,
+                   a_in + (t - a_out) * (num_frames - a_in) / (num_frames - a_out))
+    return src, np.floor(src * shift + .5).astype(np.int64)
 
 
 class STFT:
@@ -119,6 +145,34 @@ def get_fbanks(sample_rate, stft_size, number_of_filters,
     edges = edges * stft_size / sample_rate            # in (fractional) bins
     k = np.arange(stft_size // 2 + 1, dtype=np.float64)[None, :]
     lo, ce, hi = edges[:-2, None], edges[1:-1, None], edges[2:, None]
+    fb = np.maximum(np.minimum((k - lo) / (ce - lo), (hi - k) / (hi - ce)), 0.)
+    return fb / (fb.sum(-1, keepdims=True) + 1e-6)
+
+
+def warp_mel(m, alpha, ratio, m_hi):
+    """paderbox MelWarping [R] (kwargs training.py:195-208): VTLP-shaped piecewise-linear warp applied in
+    the mel domain.  m_b = m_hi / (1 + ratio); slope alpha below the knee m_b*min(alpha,1)/alpha, then a
+    straight line to (m_hi, m_hi)."""
+    m = np.asarray(m, dtype=np.float64)
+    mn = np.minimum(alpha, 1.)
+    m_b = m_hi / (1. + ratio)
+    knee = m_b * mn / alpha
+    return np.where(m <= knee, alpha * m, m_hi - (m_hi - m_b * mn) / (m_hi - knee) * (m_hi - m))
+
+
+def get_warped_fbanks(alpha, ratio, sample_rate, stft_size, number_of_filters, lowest_frequency=50.,
+                      highest_frequency=None, warp_highest_frequency=None):
+    """(B, number_of_filters, F) float64: ``get_fbanks`` on per-example warped edge frequencies."""
+    if highest_frequency is None:
+        highest_frequency = sample_rate / 2
+    if warp_highest_frequency is None:
+        warp_highest_frequency = sample_rate / 2
+    alpha = np.asarray(alpha, dtype=np.float64)[:, None]
+    ratio = np.asarray(ratio, dtype=np.float64)[:, None]
+    mel = np.linspace(hz2mel(lowest_frequency), hz2mel(highest_frequency), number_of_filters + 2)[None]
+    edges = mel2hz(warp_mel(mel, alpha, ratio, hz2mel(warp_highest_frequency))) * stft_size / sample_rate
+    k = np.arange(stft_size // 2 + 1, dtype=np.float64)[None, None, :]
+    lo, ce, hi = edges[:, :-2, None], edges[:, 1:-1, None], edges[:, 2:, None]
     fb = np.maximum(np.minimum((k - lo) / (ce - lo), (hi - k) / (hi - ce)), 0.)
     return fb / (fb.sum(-1, keepdims=True) + 1e-6)
 
@@ -329,15 +383,40 @@ class NormalizedLogMelExtractor(nn.Module):
             'bcft', (None, num_channels, number_of_filters, None), statistics_axis='bt',
             independent_axis=None, eps=norm_eps, momentum=None, interpolation_factor=1.)
 
-    def forward(self, x, seq_len=None, targets=None):
-        assert not (self.training and self.augment), 'augmentations: SURVEY 8f row 2'
+    def forward(self, x, seq_len=None, targets=None, augmentation=None):
+        """augmentation (training only; the random draws are made by the caller so that both sides of a
+        parity test see the same ones): dict with any of alpha, ratio (B,) mel warping; time_masks,
+        freq_masks (B, n, 2) int (onset, width); noise (B, C, F, T) standard normal, noise_scale (B,).
+        Order [R]: warped filterbank -> log -> running norm -> clamp -> time masks -> frequency masks ->
+        noise; frames behind seq_len stay 0."""
+        assert not (self.training and self.augment and augmentation is None), 'pass the draws explicitly'
+        aug = augmentation if (self.training and augmentation) else {}
         with torch.no_grad():
             power = (x ** 2).sum(-1)                              # b c t f
-            mel = torch.log(power @ self.fbanks + 1e-18)          # b c t m
+            if 'alpha' in aug:
+                fb = get_warped_fbanks(aug['alpha'], aug['ratio'], self.sample_rate, self.stft_size,
+                                       self.number_of_filters)
+                fb = torch.from_numpy(fb).float().transpose(1, 2)[:, None]        # b 1 f m
+                mel = torch.log(power @ fb + 1e-18)
+            else:
+                mel = torch.log(power @ self.fbanks + 1e-18)      # b c t m
             x = mel.transpose(-2, -1)                             # b c m t
             x = self.norm(x, seq_len)
             if self.clamp is not None:
                 x = torch.clamp(x, -self.clamp, self.clamp)
+            B, _, F, T = x.shape
+            for key, axis in (('time_masks', 3), ('freq_masks', 2)):
+                if key in aug:
+                    for b in range(B):
+                        for on, w in np.asarray(aug[key])[b]:
+                            if axis == 3:
+                                x[b, :, :, on:on + w] = 0.
+                            else:
+                                x[b, :, on:on + w, :] = 0.
+            if 'noise' in aug:
+                x = x + torch.as_tensor(aug['noise_scale']).float().reshape(B, 1, 1, 1) * torch.as_tensor(aug['noise']).float()
+            if aug and seq_len is not None:
+                x = x * compute_mask(x, seq_len, 0, -1)
         if targets is None:
             return x, seq_len
         return x, seq_len, targets

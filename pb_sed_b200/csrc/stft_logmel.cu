@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256)
 logmel_kernel(const float* __restrict__ src, int S, int shift, int window_length, int N,
               int pad_front, int T, int n_bins, const float* __restrict__ window,
               const int* __restrict__ fb_lo, const int* __restrict__ fb_hi,
-              const float* __restrict__ fb_w, int fb_stride, int n_mels,
+              const float* __restrict__ fb_w, int fb_stride, int n_mels, int fb_per_clip,
+              const int* __restrict__ frame_start,
               const int* __restrict__ seq_len, float* __restrict__ logmel,
               double* __restrict__ stats) {
   extern __shared__ __align__(16) float smem[];
@@ -39,6 +40,10 @@ logmel_kernel(const float* __restrict__ src, int S, int shift, int window_length
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+  if (fb_per_clip) {                       // per-example warped filterbank (train-time MelWarping)
+    fb_lo += (long long)b * n_mels; fb_hi += (long long)b * n_mels;
+    fb_w += (long long)b * n_mels * fb_stride;
+  }
 
   if (FROM_AUDIO) {
     for (int k = tid; k < N / 2; k += 256) {
@@ -59,7 +64,9 @@ logmel_kernel(const float* __restrict__ src, int S, int shift, int window_length
         float xa = 0.f, xb = 0.f;
         if (n < window_length) {
           const float w = win[n];
-          const int ia = ta * shift + n - pad_front, ib = ia + shift;
+          // frame onsets: uniform hop, or the piecewise-linear grid of TimeWarpedSTFT (transform.py:36-45)
+          const int ia = (frame_start ? __ldg(frame_start + (long long)b * T + ta) : ta * shift) + n - pad_front;
+          const int ib = (frame_start ? (tb < T ? __ldg(frame_start + (long long)b * T + tb) : 0) : tb * shift) + n - pad_front;
           if (ia >= 0 && ia < S) xa = __ldg(a + ia) * w;
           if (tb < T && ib >= 0 && ib < S) xb = __ldg(a + ib) * w;
         }
@@ -139,8 +146,8 @@ static size_t logmel_smem(bool from_audio, int N, int n_bins, int n_mels, int wi
 extern "C" int pbsed_stft_logmel(const float* audio, int B, int S, int shift, int window_length,
                                  int fft_size, int pad_front, int T, const float* window,
                                  const int* fbank_lo, const int* fbank_hi, const float* fbank_w,
-                                 int fbank_stride, int n_mels, const int* seq_len, float* logmel,
-                                 double* stats, void* stream) {
+                                 int fbank_stride, int n_mels, int fbank_per_clip, const int* frame_start,
+                                 const int* seq_len, float* logmel, double* stats, void* stream) {
   if (!audio || !window || !fbank_lo || !fbank_hi || !fbank_w || !logmel) return PBSED_EINVAL;
   if (B < 1 || S < 1 || T < 1 || shift < 1 || n_mels < 1 || B > 65535) return PBSED_EINVAL;
   if (fft_size < 8 || fft_size > 4096 || (fft_size & (fft_size - 1))) return PBSED_EINVAL;
@@ -153,14 +160,14 @@ extern "C" int pbsed_stft_logmel(const float* audio, int B, int S, int shift, in
   dim3 grid(cdiv(T, FR), B);
   logmel_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(
       audio, S, shift, window_length, fft_size, pad_front, T, n_bins, window, fbank_lo, fbank_hi,
-      fbank_w, fbank_stride, n_mels, seq_len, logmel, stats);
+      fbank_w, fbank_stride, n_mels, fbank_per_clip, frame_start, seq_len, logmel, stats);
   return pbsed_after_launch();
 }
 
 extern "C" int pbsed_spec_logmel(const float* stft, int B, int T, int n_bins, const int* fbank_lo,
                                  const int* fbank_hi, const float* fbank_w, int fbank_stride,
-                                 int n_mels, const int* seq_len, float* logmel, double* stats,
-                                 void* stream) {
+                                 int n_mels, int fbank_per_clip, const int* seq_len, float* logmel,
+                                 double* stats, void* stream) {
   if (!stft || !fbank_lo || !fbank_hi || !fbank_w || !logmel) return PBSED_EINVAL;
   if (B < 1 || T < 1 || n_bins < 1 || n_mels < 1 || B > 65535) return PBSED_EINVAL;
   const size_t smem = logmel_smem(false, 0, n_bins, n_mels, 0);
@@ -170,14 +177,18 @@ extern "C" int pbsed_spec_logmel(const float* stft, int B, int T, int n_bins, co
   dim3 grid(cdiv(T, FR), B);
   logmel_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
       stft, 0, 0, 0, 0, 0, T, n_bins, nullptr, fbank_lo, fbank_hi, fbank_w, fbank_stride, n_mels,
-      seq_len, logmel, stats);
+      fbank_per_clip, nullptr, seq_len, logmel, stats);
   return pbsed_after_launch();
 }
 
-// ------------------------------------------------------------------ normalise + clamp + mask
+// ------------------------------------------------------------------ normalise + clamp + mask (+ train-time augmentation)
+// order (SURVEY App. A [R]): running-stat normalisation -> clamp -> time masks -> frequency masks ->
+// additive Gaussian noise; frames behind seq_len stay exactly 0.
 __global__ void __launch_bounds__(256)
 logmel_normalize_kernel(float* __restrict__ x, int F, int T, const float* __restrict__ scale,
                         const float* __restrict__ shift, float clampv, const int* __restrict__ seq_len,
+                        const int* __restrict__ tmask, int n_tmask, const int* __restrict__ fmask, int n_fmask,
+                        const float* __restrict__ noise, const float* __restrict__ noise_scale,
                         long long total) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -189,6 +200,15 @@ logmel_normalize_kernel(float* __restrict__ x, int F, int T, const float* __rest
     if (t < len_b) {
       v = fmaf(x[i], __ldg(scale + f), __ldg(shift + f));
       if (clampv > 0.f) v = fminf(fmaxf(v, -clampv), clampv);
+      for (int j = 0; j < n_tmask; ++j) {
+        const int on = __ldg(tmask + ((long long)b * n_tmask + j) * 2), w = __ldg(tmask + ((long long)b * n_tmask + j) * 2 + 1);
+        if (t >= on && t < on + w) v = 0.f;
+      }
+      for (int j = 0; j < n_fmask; ++j) {
+        const int on = __ldg(fmask + ((long long)b * n_fmask + j) * 2), w = __ldg(fmask + ((long long)b * n_fmask + j) * 2 + 1);
+        if (f >= on && f < on + w) v = 0.f;
+      }
+      if (noise) v = fmaf(__ldg(noise_scale + b), __ldg(noise + i), v);
     }
     x[i] = v;
   }
@@ -196,11 +216,82 @@ logmel_normalize_kernel(float* __restrict__ x, int F, int T, const float* __rest
 
 extern "C" int pbsed_logmel_normalize(float* x, int B, int F, int T, const float* scale,
                                       const float* shift, float clampv, const int* seq_len,
+                                      const int* time_masks, int n_time_masks, const int* freq_masks,
+                                      int n_freq_masks, const float* noise, const float* noise_scale,
                                       void* stream) {
   if (!x || !scale || !shift || B < 1 || F < 1 || T < 1) return PBSED_EINVAL;
+  if ((n_time_masks > 0 && !time_masks) || (n_freq_masks > 0 && !freq_masks) || n_time_masks < 0 || n_freq_masks < 0)
+    return PBSED_EINVAL;
+  if (noise && !noise_scale) return PBSED_EINVAL;
   const long long total = (long long)B * F * T;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  logmel_normalize_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, F, T, scale, shift, clampv, seq_len, total);
+  logmel_normalize_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      x, F, T, scale, shift, clampv, seq_len, time_masks, n_time_masks, freq_masks, n_freq_masks, noise,
+      noise_scale, total);
+  return pbsed_after_launch();
+}
+
+// ------------------------------------------------------------------ per-example warped mel filterbanks
+// paderbox MelWarping [R] (configured at pb_sed/experiments/weak_label_crnn/training.py:195-208): the
+// n_mels+2 equally mel-spaced edge frequencies are warped per example, piecewise linearly in the mel
+// domain (vocal-tract-length-perturbation shape: slope alpha up to the break point, then a straight
+// line to (m_hi, m_hi)), and the unit-sum triangles are rebuilt on the warped edges.
+//   m_b = m_hi / (1 + ratio);  knee = m_b * min(alpha, 1) / alpha
+//   m' = alpha * m                                                    (m <= knee)
+//   m' = m_hi - (m_hi - m_b * min(alpha,1)) / (m_hi - knee) * (m_hi - m)   (m > knee)
+// One CTA per clip, one thread per filter; float64 like the host-side table.
+__device__ __forceinline__ double warp_mel(double m, double alpha, double m_b, double m_hi) {
+  const double mn = fmin(alpha, 1.0);
+  const double knee = m_b * mn / alpha;
+  if (m <= knee) return alpha * m;
+  return m_hi - (m_hi - m_b * mn) / (m_hi - knee) * (m_hi - m);
+}
+
+__global__ void make_warped_fbank_kernel(const float* __restrict__ alpha, const float* __restrict__ ratio,
+                                         int n_mels, int n_bins, double mel_lo, double mel_hi,
+                                         double mel_warp_hi, double bins_per_hz, int* __restrict__ lo_out,
+                                         int* __restrict__ hi_out, float* __restrict__ w_out, int stride) {
+  const int b = blockIdx.x;
+  const double a = (double)alpha[b];
+  const double m_b = mel_warp_hi / (1.0 + (double)ratio[b]);
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    double e[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double mel = mel_lo + (mel_hi - mel_lo) * (double)(m + j) / (double)(n_mels + 1);
+      const double wm = warp_mel(mel, a, m_b, mel_warp_hi);
+      e[j] = 700.0 * (pow(10.0, wm / 2595.0) - 1.0) * bins_per_hz;
+    }
+    int lo = (int)floor(e[0]) + 1, hi = (int)ceil(e[2]);
+    lo = max(lo, 0); hi = min(hi, n_bins);
+    if (hi - lo > stride) hi = lo + stride;
+    if (hi < lo) hi = lo;
+    float* w = w_out + ((long long)b * n_mels + m) * stride;
+    double sum = 0.0;
+    for (int k = lo; k < hi; ++k) {
+      const double tri = fmax(fmin(((double)k - e[0]) / (e[1] - e[0]), (e[2] - (double)k) / (e[2] - e[1])), 0.0);
+      sum += tri;
+    }
+    const double inv = 1.0 / (sum + 1e-6);
+    for (int k = lo; k < hi; ++k) {
+      const double tri = fmax(fmin(((double)k - e[0]) / (e[1] - e[0]), (e[2] - (double)k) / (e[2] - e[1])), 0.0);
+      w[k - lo] = (float)(tri * inv);
+    }
+    for (int k = hi - lo; k < stride; ++k) w[k] = 0.f;
+    lo_out[(long long)b * n_mels + m] = lo;
+    hi_out[(long long)b * n_mels + m] = hi;
+  }
+}
+
+extern "C" int pbsed_make_warped_fbank(const float* alpha, const float* ratio, int B, int n_mels, int n_bins,
+                                       double mel_lo, double mel_hi, double mel_warp_hi, double bins_per_hz,
+                                       int* fbank_lo, int* fbank_hi, float* fbank_w, int fbank_stride,
+                                       void* stream) {
+  if (!alpha || !ratio || !fbank_lo || !fbank_hi || !fbank_w) return PBSED_EINVAL;
+  if (B < 1 || n_mels < 1 || n_bins < 2 || fbank_stride < 1 || !(mel_hi > mel_lo) || !(mel_warp_hi > 0.)) return PBSED_EINVAL;
+  make_warped_fbank_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(alpha, ratio, n_mels, n_bins, mel_lo, mel_hi,
+                                                               mel_warp_hi, bins_per_hz, fbank_lo, fbank_hi,
+                                                               fbank_w, fbank_stride);
   return pbsed_after_launch();
 }

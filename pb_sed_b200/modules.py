@@ -555,6 +555,15 @@ class GRU(nn.Module):
 
 
 # =============================================================== feature extractor
+def _sampler_cfg(cfg, *names, default=None):
+    """read ``scale`` / ``truncation`` ... from a padertorch sampling-fn config dict or object."""
+    out = []
+    for n in names:
+        v = cfg.get(n, default) if isinstance(cfg, dict) else getattr(cfg, n, default)
+        out.append(v)
+    return out
+
+
 class NormalizedLogMelExtractor(nn.Module):
     """padertorch.contrib.je.modules.features.NormalizedLogMelExtractor on the GPU (kwargs
     training.py:190-217; call weak_label/crnn.py:86-90).
@@ -562,21 +571,35 @@ class NormalizedLogMelExtractor(nn.Module):
     Accepts the reference's 5-D ``stft`` (B,1,T,F,2) OR the raw waveform (B,1,S) / (B,S), in which
     case the STFT of ``data_preparation/provider.py:315-323`` (``stft_kwargs``) runs fused in the same
     kernel.  Output (B,1,n_mels,T): log-mel, cumulative running mean/var normalisation per band
-    (eps 1e-5, no affine), clamp(+-6), padded frames zeroed.  The train-only random augmentations
-    (mel warping, time/frequency masks, noise) are SURVEY 8f row 2 and are not applied; the
-    kwargs are accepted so that the reference config instantiates unchanged.
+    (eps 1e-5, no affine), clamp(+-6), padded frames zeroed.
+
+    Train-time augmentation (all random draws are made ON THE DEVICE with torch's
+    generator, so the step stays CUDA-graph capturable, and are kept in ``last_augmentation``):
+      * ``frequency_warping_fn`` = MelWarping config (training.py:195-208): per-example warped
+        filterbanks, built by ``pbsed_make_warped_fbank`` and consumed by the fused STFT/mel kernel;
+      * ``n_time_masks`` / ``n_frequency_masks`` (+ max steps / rates, training.py:210-215) and
+        ``max_noise_scale`` (:216): fused into the normalise/clamp pass;
+      * ``time_warping`` = dict(anchor=(.4,.6), anchor_shift=(-.1,.1)) (provider.py:329-338, the
+        TimeWarpedSTFT wrapper of transform.py:36-45): non-uniform frame onsets inside the STFT kernel
+        (raw-audio input only); frame-level targets are re-sampled on the same grid.
     """
 
     def __init__(self, sample_rate, stft_size, number_of_filters, num_channels=1,
                  lowest_frequency=50., highest_frequency=None, add_deltas=False,
-                 add_delta_deltas=False, norm_eps=1e-5, clamp=6., stft_kwargs=None, **augment_kwargs):
+                 add_delta_deltas=False, norm_eps=1e-5, clamp=6., stft_kwargs=None,
+                 frequency_warping_fn=None, blur_sigma=0., n_time_masks=0, max_masked_time_steps=70,
+                 max_masked_time_rate=.2, n_frequency_masks=0, max_masked_frequency_bands=20,
+                 max_masked_frequency_rate=.2, max_noise_scale=0., time_warping=None, **unused):
         super().__init__()
         if add_deltas or add_delta_deltas or num_channels != 1:
             raise NotImplementedError('deltas / multi-channel input are off on the hot path')
+        if blur_sigma:
+            raise NotImplementedError('blur_sigma is commented out in the reference config (training.py:209)')
         self.sample_rate, self.stft_size, self.number_of_filters = sample_rate, stft_size, number_of_filters
         self.add_deltas, self.add_delta_deltas = add_deltas, add_delta_deltas
         self.norm_eps, self.clamp = norm_eps, clamp
-        self.augment_kwargs = augment_kwargs
+        self.lowest_frequency = lowest_frequency
+        self.highest_frequency = sample_rate / 2 if highest_frequency is None else highest_frequency
         fb = mel_filterbank(sample_rate, stft_size, number_of_filters, lowest_frequency, highest_frequency)
         self.register_buffer('fbanks', torch.from_numpy(fb.T.copy()).float())          # (F, n_mels)
         lo, hi, w, stride = sparse_filterbank(fb.astype(np.float32))
@@ -594,38 +617,128 @@ class NormalizedLogMelExtractor(nn.Module):
         self.norm = Normalization(number_of_filters, 2, eps=norm_eps, momentum=-1., affine=False)
         # reference buffer shape is (1, 1, n_mels, 1): statistics axis 'bt' of 'bcft'
         self.norm._ref_shape = lambda: (1, 1, number_of_filters, 1)
+        # ---- augmentation config
+        self.warping = None
+        if frequency_warping_fn is not None:
+            wf, bf, hf = _sampler_cfg(frequency_warping_fn, 'warp_factor_sampling_fn',
+                                      'boundary_frequency_ratio_sampling_fn', 'highest_frequency')
+            (w_scale, w_trunc), (b_scale, b_trunc) = _sampler_cfg(wf, 'scale', 'truncation'), _sampler_cfg(bf, 'scale', 'truncation')
+            self.warping = dict(scale=float(w_scale), truncation=float(w_trunc), ratio_scale=float(b_scale),
+                                ratio_truncation=float(b_trunc),
+                                highest_frequency=float(hf if hf is not None else sample_rate / 2))
+        self.n_time_masks, self.max_masked_time_steps, self.max_masked_time_rate = \
+            n_time_masks, max_masked_time_steps, max_masked_time_rate
+        self.n_frequency_masks, self.max_masked_frequency_bands, self.max_masked_frequency_rate = \
+            n_frequency_masks, max_masked_frequency_bands, max_masked_frequency_rate
+        self.max_noise_scale = max_noise_scale
+        self.time_warping = time_warping
+        self.last_augmentation = None
+        self.next_augmentation = None      # test hook: draws to use instead of sampling (consumed once)
 
     def _fb(self):
         return dict(lo=self._fb_lo, hi=self._fb_hi, w=self._fb_w, stride=self._fb_stride,
                     n_mels=self.number_of_filters)
 
+    def augments(self):
+        return bool(self.warping or self.n_time_masks or self.n_frequency_masks or self.max_noise_scale
+                    or self.time_warping)
+
+    # ---- random draws (device-side, graph capturable)
+    @staticmethod
+    def _masks(n, lens, max_steps, max_rate, dev):
+        """(B, n, 2) int32 (onset, width): width ~ U{0..min(max_steps, floor(rate*len))}, onset ~ U{0..len-width}."""
+        B = lens.shape[0]
+        max_w = torch.minimum(torch.full_like(lens, float(max_steps)), torch.floor(lens * max_rate))
+        w = torch.floor(torch.rand((B, n), device=dev) * (max_w[:, None] + 1.)).clamp_(max=max_w[:, None])
+        on = torch.floor(torch.rand((B, n), device=dev) * (lens[:, None] - w + 1.)).clamp_(max=(lens[:, None] - w))
+        return torch.stack([on, w], -1).to(torch.int32).contiguous()
+
+    def sample_augmentation(self, B, T, seq, dev, from_audio):
+        aug = {}
+        if self.warping:
+            c = self.warping
+            a = c['truncation'] / c['scale']
+            p_lo = .5 * (1. + math.erf(-a / math.sqrt(2.)))
+            u = p_lo + torch.rand(B, device=dev) * (1. - 2. * p_lo)
+            z = math.sqrt(2.) * torch.erfinv((2. * u - 1.).clamp(-1. + 1e-7, 1. - 1e-7))
+            aug['alpha'] = torch.exp(c['scale'] * z.clamp(-a, a))                        # LogTruncatedNormal
+            u = torch.rand(B, device=dev)
+            aug['ratio'] = -c['ratio_scale'] * torch.log1p(-u * (1. - math.exp(-c['ratio_truncation'] / c['ratio_scale'])))
+        lens = seq.dev.float() if seq.dev is not None else torch.full((B,), float(T), device=dev)
+        if self.n_time_masks:
+            aug['time_masks'] = self._masks(self.n_time_masks, lens, self.max_masked_time_steps,
+                                            self.max_masked_time_rate, dev)
+        if self.n_frequency_masks:
+            bands = torch.full((B,), float(self.number_of_filters), device=dev)
+            aug['freq_masks'] = self._masks(self.n_frequency_masks, bands, self.max_masked_frequency_bands,
+                                            self.max_masked_frequency_rate, dev)
+        if self.max_noise_scale:
+            aug['noise_scale'] = torch.rand(B, device=dev) * self.max_noise_scale
+            aug['noise'] = torch.randn((B, self.number_of_filters, T), device=dev)
+        if self.time_warping and from_audio:
+            (a0, a1), (s0, s1) = self.time_warping['anchor'], self.time_warping['anchor_shift']
+            aug['anchor'] = a0 + torch.rand(B, device=dev) * (a1 - a0)
+            aug['anchor_shift'] = s0 + torch.rand(B, device=dev) * (s1 - s0)
+        return aug
+
+    def _time_warp_grid(self, aug, T, shift):
+        """source position (frames, float64) and first sample (int32) of every output frame."""
+        a_in = aug['anchor'].double()[:, None] * T
+        a_out = ((aug['anchor'] + aug['anchor_shift']).double()[:, None] * T).clamp(1., T - 1.)
+        t = torch.arange(T, device=a_in.device, dtype=torch.float64)[None]
+        src = torch.where(t <= a_out, t * a_in / a_out, a_in + (t - a_out) * (T - a_in) / (T - a_out))
+        return src, torch.floor(src * shift + .5).to(torch.int32).contiguous()
+
     def forward(self, x, seq_len=None, targets=None):
         with torch.no_grad():
             n = self.norm
             train = self.training
-            if x.dim() == 5:
-                B, C, T = x.shape[:3]
-                assert C == 1
-                seq = SeqLen.make(seq_len, B, T, x.device)
-                stats = ops._stats_buffer(self.number_of_filters, x.device) if train else None
-                y = ops.logmel_from_stft(x.reshape(B, T, x.shape[3], 2), self._fb(), seq, stats)
-            else:
+            from_audio = x.dim() != 5
+            if from_audio:
                 a = x.reshape(x.shape[0], -1)
                 B, S = a.shape
                 kw = self.stft_kwargs
                 T = stft_num_frames(S, kw['shift'], kw['window_length'], kw['fading'], kw['pad'])
+            else:
+                B, C, T = x.shape[:3]
+                assert C == 1
+            seq = SeqLen.make(seq_len, B, T, x.device)
+            aug = {}
+            if train and self.augments():
+                aug = self.next_augmentation if self.next_augmentation is not None \
+                    else self.sample_augmentation(B, T, seq, x.device, from_audio)
+                self.next_augmentation = None
+            self.last_augmentation = aug
+            fb = self._fb()
+            if 'alpha' in aug:
+                c = self.warping
+                fb = ops.make_warped_fbank(aug['alpha'], aug['ratio'], self.number_of_filters, self.stft_size // 2 + 1,
+                                           float(hz2mel(self.lowest_frequency)), float(hz2mel(self.highest_frequency)),
+                                           float(hz2mel(c['highest_frequency'])), self.stft_size / self.sample_rate,
+                                           self.stft_size // 2 + 1)
+            stats = ops._stats_buffer(self.number_of_filters, x.device) if train else None
+            if from_audio:
                 pad_front = {'half': (kw['window_length'] - kw['shift']) // 2, 'full': kw['window_length'] - kw['shift'],
                              True: kw['window_length'] - kw['shift']}.get(kw['fading'], 0)
-                seq = SeqLen.make(seq_len, B, T, x.device)
-                stats = ops._stats_buffer(self.number_of_filters, x.device) if train else None
                 cfg = dict(shift=kw['shift'], window_length=kw['window_length'], size=kw['size'],
                            pad_front=pad_front, T=T, window=self._window)
-                y = ops.logmel_from_audio(a, cfg, self._fb(), seq, stats)
+                frame_start = None
+                if 'anchor' in aug:
+                    src, frame_start = self._time_warp_grid(aug, T, kw['shift'])
+                    if targets is not None:     # frame-level targets follow the warped grid (nearest frame)
+                        idx = torch.floor(src + .5).long().clamp_(0, T - 1)
+                        targets = tuple(tg if tg.dim() < 3 else
+                                        torch.gather(tg, 2, idx[:, None, :].expand(-1, tg.shape[1], -1))
+                                        for tg in targets)
+                y = ops.logmel_from_audio(a, cfg, fb, seq, stats, frame_start)
+            else:
+                y = ops.logmel_from_stft(x.reshape(B, T, x.shape[3], 2), fb, seq, stats)
             count = ops._sync_count_(stats, self.number_of_filters, seq.frames()) if train else 1.
             scale, shift = ops.norm_finalize(stats, count, self.number_of_filters,
                                              None, None, n.eps, -1., train, n.running_mean,
                                              n.running_power, n.num_tracked_values, x.device)
-            ops.logmel_normalize_(y, scale, shift, self.clamp, seq)
+            ops.logmel_normalize_(y, scale, shift, self.clamp, seq, aug.get('time_masks'), aug.get('freq_masks'),
+                                  aug.get('noise'), aug.get('noise_scale'))
             y = y.unsqueeze(1)                                            # (B,1,n_mels,T)
         if targets is None:
             return y, seq_len

@@ -607,16 +607,17 @@ class BicrnnLossFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------ features
-def logmel_from_audio(audio, stft_cfg, fb, seq, stats):
-    """audio (B,S) -> log-mel (B, n_mels, T) (+ accumulates per-band stats)."""
+def logmel_from_audio(audio, stft_cfg, fb, seq, stats, frame_start=None):
+    """audio (B,S) -> log-mel (B, n_mels, T) (+ accumulates per-band stats).  ``fb['per_clip']``: one
+    filterbank per clip (MelWarping); ``frame_start`` int32 (B,T): TimeWarpedSTFT frame onsets."""
     audio = _f32c(audio)
     B, S = audio.shape
     T = stft_cfg['T']
     out = torch.empty((B, fb['n_mels'], T), device=audio.device)
     call('pbsed_stft_logmel', _ptr(audio), B, S, stft_cfg['shift'], stft_cfg['window_length'],
          stft_cfg['size'], stft_cfg['pad_front'], T, _ptr(stft_cfg['window']), _ptr(fb['lo']),
-         _ptr(fb['hi']), _ptr(fb['w']), fb['stride'], fb['n_mels'], seq.ptr, _ptr(out),
-         _ptr(stats), _stream())
+         _ptr(fb['hi']), _ptr(fb['w']), fb['stride'], fb['n_mels'], int(fb.get('per_clip', False)),
+         _ptr(frame_start), seq.ptr, _ptr(out), _ptr(stats), _stream())
     return out
 
 
@@ -627,8 +628,20 @@ def logmel_from_stft(stft, fb, seq, stats):
     assert two == 2
     out = torch.empty((B, fb['n_mels'], T), device=stft.device)
     call('pbsed_spec_logmel', _ptr(stft), B, T, n_bins, _ptr(fb['lo']), _ptr(fb['hi']), _ptr(fb['w']),
-         fb['stride'], fb['n_mels'], seq.ptr, _ptr(out), _ptr(stats), _stream())
+         fb['stride'], fb['n_mels'], int(fb.get('per_clip', False)), seq.ptr, _ptr(out), _ptr(stats), _stream())
     return out
+
+
+def make_warped_fbank(alpha, ratio, n_mels, n_bins, mel_lo, mel_hi, mel_warp_hi, bins_per_hz, stride):
+    """per-example warped filterbank tables (B = len(alpha)) for ``logmel_from_*`` (``per_clip``)."""
+    B = alpha.shape[0]
+    dev = alpha.device
+    lo = torch.empty((B, n_mels), device=dev, dtype=torch.int32)
+    hi = torch.empty((B, n_mels), device=dev, dtype=torch.int32)
+    w = torch.empty((B, n_mels, stride), device=dev)
+    call('pbsed_make_warped_fbank', _ptr(_f32c(alpha)), _ptr(_f32c(ratio)), B, n_mels, n_bins, float(mel_lo),
+         float(mel_hi), float(mel_warp_hi), float(bins_per_hz), _ptr(lo), _ptr(hi), _ptr(w), stride, _stream())
+    return dict(lo=lo, hi=hi, w=w, stride=stride, n_mels=n_mels, per_clip=True)
 
 
 def norm_finalize(stats, count, nch, gamma, beta, eps, momentum, training, rmean, rpower, ntracked,
@@ -641,8 +654,13 @@ def norm_finalize(stats, count, nch, gamma, beta, eps, momentum, training, rmean
     return scale, shift
 
 
-def logmel_normalize_(x, scale, shift, clamp, seq):
+def logmel_normalize_(x, scale, shift, clamp, seq, time_masks=None, freq_masks=None, noise=None,
+                      noise_scale=None):
+    """in place: normalise, clamp, zero padded frames; train-time: (B,n,2) int32 time / frequency masks
+    and ``noise_scale[b] * noise``."""
     B, F, T = x.shape
+    nt = 0 if time_masks is None else time_masks.shape[1]
+    nf = 0 if freq_masks is None else freq_masks.shape[1]
     call('pbsed_logmel_normalize', _ptr(x), B, F, T, _ptr(scale), _ptr(shift), float(clamp or 0.),
-         seq.ptr, _stream())
+         seq.ptr, _ptr(time_masks), nt, _ptr(freq_masks), nf, _ptr(noise), _ptr(noise_scale), _stream())
     return x

@@ -341,3 +341,107 @@ def test_graphed_train_step_equals_eager():
         # mathematically zero gradient (conv bias in front of a batch norm) into +-lr steps, so the two
         # trajectories are compared on what is well-posed: loss and gradient norm
         assert abs(float(l1) - float(l2)) < 1e-4 and abs(float(g1) - float(g2)) < 1e-2 * float(g1)
+
+
+# ------------------------------------------------------------------ train-time feature augmentation
+AUG_KW = dict(
+    frequency_warping_fn={'factory': 'MelWarping',
+                          'warp_factor_sampling_fn': {'factory': 'LogTruncatedNormal', 'scale': .08, 'truncation': np.log(1.3)},
+                          'boundary_frequency_ratio_sampling_fn': {'factory': 'TruncatedExponential', 'scale': .5, 'truncation': 5.},
+                          'highest_frequency': 8000.},
+    n_time_masks=1, max_masked_time_steps=70, max_masked_time_rate=.2,
+    n_frequency_masks=1, max_masked_frequency_bands=20, max_masked_frequency_rate=.2, max_noise_scale=.2)
+
+
+def _aug_np(aug):
+    return {k: v.detach().cpu().numpy() for k, v in aug.items()}
+
+
+def test_warped_filterbank_tables_match_oracle():
+    from pb_sed_b200 import ops
+    from pb_sed_b200.modules import hz2mel
+    alpha = torch.tensor([1., 1.29, .78, 1.1, .9], device=DEV)
+    ratio = torch.tensor([.5, .01, 4.9, 1.5, .02], device=DEV)
+    fb = ops.make_warped_fbank(alpha, ratio, 128, 513, float(hz2mel(50.)), float(hz2mel(8000.)), float(hz2mel(8000.)),
+                               1024 / 16000, 513)
+    ref = P.get_warped_fbanks(alpha.cpu().numpy(), ratio.cpu().numpy(), 16000, 1024, 128)
+    dense = np.zeros_like(ref)
+    lo, hi, w = fb['lo'].cpu().numpy(), fb['hi'].cpu().numpy(), fb['w'].cpu().numpy()
+    for b in range(5):
+        for m in range(128):
+            dense[b, m, lo[b, m]:hi[b, m]] = w[b, m, :hi[b, m] - lo[b, m]]
+    assert np.abs(dense - ref).max() < 1e-6
+    assert np.abs(dense[0] - P.get_fbanks(16000, 1024, 128)).max() < 1e-6      # alpha = 1: the plain filterbank
+
+
+@pytest.mark.parametrize('from_audio', [True, False])
+def test_feature_augmentation_matches_oracle_with_the_same_draws(from_audio):
+    from pb_sed_b200.modules import NormalizedLogMelExtractor
+    kw = dict(shift=320, window_length=960, size=1024)
+    audio = OM.synthetic_audio(3, 16000, seed=5)
+    T = P.stft_frames(16000, 320, 960)
+    seq_len = np.array([T, T - 3, T // 2])
+    torch.manual_seed(3)
+    fe = NormalizedLogMelExtractor(16000, 1024, 128, stft_kwargs=kw, **AUG_KW,
+                                   time_warping=dict(anchor=(.4, .6), anchor_shift=(-.1, .1))).to(DEV).train()
+    weak, boundary = OM.synthetic_targets(3, 10, T, seed=5, seq_len=seq_len)
+    targets = (torch.from_numpy(weak).to(DEV), torch.from_numpy(boundary).to(DEV))
+    if from_audio:
+        y, _, tg = fe(torch.from_numpy(audio).to(DEV), seq_len=seq_len, targets=targets)
+    else:
+        spec = P.stft(audio, **kw)
+        stft = torch.from_numpy(np.stack([spec.real, spec.imag], -1).astype(np.float32))
+        y, _, tg = fe(stft.to(DEV), seq_len=seq_len, targets=targets)
+    aug = _aug_np(fe.last_augmentation)
+    # the draws respect the configured supports
+    assert (aug['alpha'] >= 1 / 1.3 - 1e-6).all() and (aug['alpha'] <= 1.3 + 1e-6).all()
+    assert (aug['ratio'] >= 0).all() and (aug['ratio'] <= 5.).all()
+    tm, fm = aug['time_masks'], aug['freq_masks']
+    assert (tm[..., 1] <= np.minimum(70, np.floor(.2 * seq_len))[:, None]).all() and (tm.sum(-1) <= seq_len[:, None]).all()
+    assert (fm[..., 1] <= 20).all() and (fm.sum(-1) <= 128).all() and (tm >= 0).all() and (fm >= 0).all()
+    assert (aug['noise_scale'] >= 0).all() and (aug['noise_scale'] <= .2).all()
+    # oracle with the same draws
+    ora = P.NormalizedLogMelExtractor(16000, 1024, 128, augment=True).train()
+    oaug = dict(aug, noise=aug['noise'][:, None])
+    if from_audio:
+        src, fs = P.time_warp_grid(aug['anchor'], aug['anchor_shift'], T, 320)
+        spec = P.stft(audio, frame_start=fs, **kw)
+        stft = torch.from_numpy(np.stack([spec.real, spec.imag], -1).astype(np.float32))
+        idx = np.clip(np.floor(src + .5).astype(int), 0, T - 1)
+        b_ref = np.take_along_axis(boundary, idx[:, None, :].repeat(10, 1), axis=2)
+        assert np.array_equal(tg[1].cpu().numpy(), b_ref) and np.array_equal(tg[0].cpu().numpy(), weak)
+    else:
+        assert 'anchor' not in aug and tg[1] is targets[1]
+    y_ref, _ = ora(stft, seq_len=seq_len, augmentation=oaug)
+    # fp32 FFT on the GPU vs float64 rfft: 2e-3 (as the un-augmented test); same fp32 STFT in: 1e-4
+    assert maxdiff(y, y_ref) < (2e-3 if from_audio else 1e-4)
+    masked = y.cpu().numpy()[0, 0]
+    on, w = tm[0, 0]
+    if w:   # masked frames carry nothing but the noise
+        assert np.abs(masked[:, on:on + w] - aug['noise_scale'][0] * aug['noise'][0][:, on:on + w]).max() < 1e-6
+    # eval mode: no augmentation, no draws
+    fe.eval()
+    fe(torch.from_numpy(audio).to(DEV), seq_len=seq_len)
+    assert fe.last_augmentation == {}
+
+
+def test_augmented_train_step_is_graph_capturable():
+    """device-side draws: the whole augmented step replays as a CUDA graph with fresh draws per replay."""
+    from pb_sed_b200 import config, train
+    from pb_sed_b200.models import weak_label
+    cfg = config.tiny_fbcrnn_config()
+    cfg['feature_extractor'].update(dict(AUG_KW, max_masked_time_steps=8, max_masked_frequency_bands=4,
+                                         time_warping=dict(anchor=(.4, .6), anchor_shift=(-.1, .1))))
+    cfg['feature_extractor']['frequency_warping_fn'] = dict(AUG_KW['frequency_warping_fn'], highest_frequency=8000.)
+    torch.manual_seed(0)
+    model = weak_label.CRNN.from_config_dict(cfg).to(DEV)
+    model.emit_buffers = False
+    opt = train.Adam(model, lr=5e-4)
+    batch = OM.synthetic_batch(4, num_samples=16 * 40 + 5, stft_kwargs=TINY_STFT, seq_len=[41, 40, 33, 17])
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'stft'}
+    step = train.GraphedTrainStep(model, opt, gb, warmup=1)
+    losses = []
+    for _ in range(3):
+        loss, _ = step(gb)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and len(set(losses)) == 3, losses
