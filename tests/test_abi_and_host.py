@@ -28,7 +28,9 @@ def test_bad_arguments_return_einval_without_touching_the_gpu(built_lib):
     d.ntaps = 99
     assert built_lib.pbsed_tapgemm_wgrad(ctypes.byref(d), None, None, None, None, None, 0, None, None, None) == -1
     assert built_lib.pbsed_gru_fwd(None, None, None, None, 1, 1, 48, 1, None, None, 48, None, None) == -1
-    assert built_lib.pbsed_stft_logmel(None, 1, 1, 1, 1, 8, 0, 1, None, None, None, None, 1, 1, None, None, None, None) == -1
+    assert built_lib.pbsed_stft_logmel(None, 1, 1, 1, 1, 8, 0, 1, None, None, None, None, 1, 1, 0, None, None, None, None, None) == -1
+    assert built_lib.pbsed_medfilt(None, 1, 1, None, 1, None, 1, None, None) == -1
+    assert built_lib.pbsed_make_warped_fbank(None, None, 1, 1, 2, 0., 1., 1., 1., None, None, None, 1, None) == -1
     with pytest.raises(_lib.PbsedError):
         _lib.call('pbsed_adam_step', None, None, None, None, 0, None, None, None, 0, None)
 
