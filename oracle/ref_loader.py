@@ -66,7 +66,7 @@ _loaded = {}
 
 def load():
     """returns (weak_label_crnn_module, strong_label_crnn_module)."""
-    if _loaded:
+    if 'weak' in _loaded:
         return _loaded['weak'], _loaded['strong']
     assert reference_available(), REFERENCE_ROOT
     if not hasattr(np, 'int'):       # pb_sed uses the removed alias (weak_label/crnn.py:252)
