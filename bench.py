@@ -303,9 +303,16 @@ def run_gpu(args):
         gemm_fl = sum(agg[k]['flop'] for k in ('pbsed_tapgemm', 'pbsed_tapgemm_wgrad') if k in agg)
         name, r = top
         achieved = r['flop'] / (r['ms'] / 1e3) / 1e12 if r['flop'] else None
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath)).get(name)
+            if tj:
+                traffic, traffic_src = tj['bytes_per_launch'], tj['source']
         out['roofline'] = {
             'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_sus, 'unit': 'TFLOP/s',
-            'frac': (achieved / tf_sus) if achieved else None, 'traffic': None,
+            'frac': (achieved / tf_sus) if achieved else None, 'traffic': traffic, 'traffic_source': traffic_src,
+            'executed_tensor_tflops': (3. * achieved if (achieved and args.precision == 'tf32x3') else achieved),
             'peak_source': f'{which} bf16 dense sustained (MEASURED_PEAKS.json); the fp32 config runs '
                            f'{args.precision} arithmetic, TF32 nominal peak is half of bf16',
             'avg_launch_ms': r['ms'] / r['calls'], 'launches_per_step': r['calls'],
@@ -316,6 +323,17 @@ def run_gpu(args):
                                           'tflops': round(v['flop'] / (v['ms'] / 1e3) / 1e12, 2) if v['flop'] else None}
                                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])}
         out['eager_step_ms'] = eager_ms
+        # per-stage rooflines the north star asks for (BASELINE.md algorithmic bytes per clip)
+        st = {}
+        if 'pbsed_stft_logmel' in agg:
+            gbs = 896000. * B / (agg['pbsed_stft_logmel']['ms'] / 1e3) / 1e9
+            st['stft_logmel'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                                 'note': 'fp32 FFT: issue-bound (profiles/r01_s4_logmel1024_ncu_full.txt), see DESIGN.md'}
+        if 'pbsed_gru_fwd' in agg:
+            gbs = 8.19e6 * B / (agg['pbsed_gru_fwd']['ms'] / 1e3) / 1e9
+            st['gru_fwd'] = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                             'note': '500 dependent time steps per layer: latency-bound'}
+        out['stage_rooflines'] = st
         if not args.no_cpu_baseline:
             v, ms, cores, cb = cpu_reference_run(3, 1)
             out['cpu_baseline'] = {'value': v, 'unit': '10s-clips/s', 'cores': cores, 'kind': 'port',
@@ -324,6 +342,94 @@ def run_gpu(args):
         print(json.dumps(out))
     if world > 1:
         step.close()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ BASELINE configs[3]
+def run_bicrnn_infer(args):
+    """strong_label_crnn tag-conditioned BiCRNN inference (BASELINE.json configs[3]): frame-score
+    throughput, eval mode, raw audio in, scores + post-processing out.  N > 1: independent replicas
+    (clips shard, no collective)."""
+    import torch
+    from pb_sed_b200 import _lib, config, ops, filters as GF
+    from pb_sed_b200.models import strong_label
+    _lib.load()
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    ops.set_default_precision(args.precision)
+    B = args.batch if args.batch != 32 else 512
+    torch.manual_seed(0)
+    model = strong_label.CRNN.from_config_dict(config.bicrnn_config(num_events=NUM_EVENTS)).to(dev).eval()
+    chunk = 64
+    host = []
+    for i in range(2):
+        audio, weak, _ = synthetic_clips(chunk, 77 + i + 10 * rank)
+        audio = np.tile(audio, (B // chunk, 1, 1))
+        host.append({'audio_data': torch.from_numpy(audio).pin_memory(),
+                     'tag_condition': torch.from_numpy(np.tile(weak, (B // chunk, 1)) > .5).pin_memory()})
+    seq_len = [T_FRAMES] * B
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    med = np.array(NUM_EVENTS * [21])
+
+    def infer(batch):
+        with torch.no_grad():
+            y, sl = model.sound_event_detection(dict(batch, seq_len=seq_len))
+            return GF.post_process(y.contiguous(), sl, medfilt_length=med)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = _lib.launch_count()
+    for i in range(max(args.warmup, 3)):
+        infer(resident[i % 2])
+    sync()
+    launches = (_lib.launch_count() - n0) // max(args.warmup, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0.record()
+    for i in range(args.steps):
+        infer(resident[i % 2])
+    e1.record()
+    sync()
+    clocks = sampler.result()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    out_host = torch.empty((B, NUM_EVENTS, T_FRAMES)).pin_memory()
+    e0.record()
+    for i in range(args.steps):
+        out_host.copy_(infer({k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}), non_blocking=True)
+    e1.record()
+    sync()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        v = world * B * args.steps / (float(ms) / 1e3)
+        print(json.dumps({
+            'metric': 'bicrnn_inference_clips_per_sec', 'value': v, 'unit': '10s-clips/s', 'frames_per_sec': v * T_FRAMES,
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': float(ms) / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)' if args.precision != 'fp32' else 'f32',
+            'data': 'synthetic',
+            'config': {'workload': f'BASELINE configs[3]: strong_label tag-conditioned BiCRNN inference, batch {B}/GPU of '
+                                   '10 s / 16 kHz clips, eval mode, raw audio -> frame scores -> sequence mask + '
+                                   'median filter (21) on the GPU', 'parallelism': f'replicas x{world}',
+                       'l2': 'per-step activations (GBs) >> 126 MB L2; 2 input batches rotate'},
+            'e2e': {'value': world * B * args.steps / (float(ms2) / 1e3), 'unit': '10s-clips/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': out_host.numel() * 4},
+            'gpu_launches': launches * args.steps, 'clocks': clocks}))
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
@@ -337,12 +443,16 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='fbcrnn_train', choices=['fbcrnn_train', 'bicrnn_infer'],
+                    help='fbcrnn_train = BASELINE configs[1] (the headline); bicrnn_infer = configs[3]')
     ap.add_argument('--sync-stats', default='none', choices=['none', 'exact'],
                     help="N > 1: per-replica batch statistics ('none') or all-reduced ('exact', SURVEY 8e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'bicrnn_infer':
+        run_bicrnn_infer(args)
     else:
         run_gpu(args)
 

@@ -135,6 +135,161 @@ logmel_kernel(const float* __restrict__ src, int S, int shift, int window_length
   }
 }
 
+// ------------------------------------------------------------------ N = 1024 fast path (the reference's STFT size)
+// One WARP transforms one frame pair: 1024 = 32 x 32 Cooley-Tukey with both 32-point stages fully
+// unrolled in registers (64 data registers per thread), one padded shared-memory transpose between
+// them, exact twiddles from a shared table.  No block-wide barrier inside the transform; 8 warps per
+// CTA cover 32 consecutive frames so the (B, n_mels, T) stores are 128-byte rows.
+constexpr int FW_WARPS = 8;
+constexpr int FW_TP = 33;                // transpose pitch in float2
+
+__device__ __forceinline__ constexpr int brev5(int i) {
+  return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// in place, natural order in, bit-reversed order out (X[k] = v[brev5(k)]); radix-2 DIF, constants folded
+__device__ __forceinline__ void fft32_regs(float2 (&v)[32]) {
+  constexpr float C[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                           0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f,
+                           0.f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f,
+                           -0.70710678118654757f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+  constexpr float S[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                           0.70710678118654757f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                           1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                           0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f};
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int half = 16 >> s;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int grp = i / half, j = i % half;
+      const int a = grp * 2 * half + j, b = a + half;
+      const int tw = j * (16 / half);
+      const float2 u = v[a], w = v[b];
+      v[a] = make_float2(u.x + w.x, u.y + w.y);
+      const float dx = u.x - w.x, dy = u.y - w.y;
+      if (tw == 0) v[b] = make_float2(dx, dy);
+      else if (tw == 8) v[b] = make_float2(dy, -dx);               // * (-i)
+      else v[b] = make_float2(dx * C[tw] + dy * S[tw], dy * C[tw] - dx * S[tw]);   // * (C - iS)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32)
+logmel1024_kernel(const float* __restrict__ src, int S, int shift, int window_length, int pad_front, int T,
+                  const float* __restrict__ window, const int* __restrict__ fb_lo,
+                  const int* __restrict__ fb_hi, const float* __restrict__ fb_w, int fb_stride, int n_mels,
+                  int fb_per_clip, const int* __restrict__ frame_start, const int* __restrict__ seq_len,
+                  float* __restrict__ logmel, double* __restrict__ stats) {
+  constexpr int N = 1024, NB = 513;
+  extern __shared__ __align__(16) float smem[];
+  float2* twid = reinterpret_cast<float2*>(smem);                       // [1024]  W_1024^i
+  float* win = smem + 2 * N;                                            // [1024]
+  float* outb = win + N;                                                // [n_mels][FR+1]
+  float2* tbuf = reinterpret_cast<float2*>(outb + n_mels * (FR + 1) + ((n_mels * (FR + 1)) & 1));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float2* tb_w = tbuf + warp * (32 * FW_TP);
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FR;
+  const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+  if (fb_per_clip) {
+    fb_lo += (long long)b * n_mels; fb_hi += (long long)b * n_mels;
+    fb_w += (long long)b * n_mels * fb_stride;
+  }
+  for (int i = tid; i < N; i += FW_WARPS * 32) {
+    float sn, cs;
+    sincospif(-2.f * (float)i / (float)N, &sn, &cs);
+    twid[i] = make_float2(cs, sn);
+    win[i] = i < window_length ? __ldg(window + i) : 0.f;
+  }
+  __syncthreads();
+  const float* a = src + (long long)b * S;
+#pragma unroll 1
+  for (int pr = warp; pr < FR / 2; pr += FW_WARPS) {
+    const int ta = t0 + 2 * pr, tb = ta + 1;
+    if (ta >= T) break;                                                 // uniform within the warp
+    const int sa = (frame_start ? __ldg(frame_start + (long long)b * T + ta) : ta * shift) - pad_front;
+    const int sb = tb < T ? (frame_start ? __ldg(frame_start + (long long)b * T + tb) : tb * shift) - pad_front : -(1 << 30);
+    float2 v[32];
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) {
+      const int n = 32 * n1 + lane;
+      const float w = win[n];
+      const int ia = sa + n, ib = sb + n;
+      const float xa = (ia >= 0 && ia < S) ? __ldg(a + ia) : 0.f;
+      const float xb = (ib >= 0 && ib < S) ? __ldg(a + ib) : 0.f;
+      v[n1] = make_float2(xa * w, xb * w);
+    }
+    fft32_regs(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const float2 y = v[brev5(k1)], w = twid[(lane * k1) & (N - 1)];
+      tb_w[k1 * FW_TP + lane] = make_float2(y.x * w.x - y.y * w.y, y.x * w.y + y.y * w.x);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = tb_w[lane * FW_TP + n2];
+    __syncwarp();
+    fft32_regs(v);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) tb_w[lane + 32 * k2] = v[brev5(k2)];   // X[k1 + 32 k2], k1 = lane
+    __syncwarp();
+    // separate the two real spectra and take |.|^2 (bins k = lane + 32 j <= 512)
+    float pa[17], pb[17];
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int k = lane + 32 * j;
+      pa[j] = pb[j] = 0.f;
+      if (k < NB) {
+        const float2 zk = tb_w[k], zn = tb_w[(N - k) & (N - 1)];
+        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+        const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+        pa[j] = ar * ar + ai * ai;
+        pb[j] = br * br + bi * bi;
+      }
+    }
+    __syncwarp();
+    float* P = reinterpret_cast<float*>(tb_w);
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+      const int k = lane + 32 * j;
+      if (k < NB) { P[k] = pa[j]; P[NB + k] = pb[j]; }
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * n_mels; i += 32) {
+      const int which = i / n_mels, m = i - which * n_mels;
+      const int lo = __ldg(fb_lo + m), hi = __ldg(fb_hi + m);
+      const float* w = fb_w + (long long)m * fb_stride;
+      const float* pp = P + which * NB;
+      float acc = 0.f;
+      for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(w + (k - lo)), pp[k], acc);
+      outb[m * (FR + 1) + 2 * pr + which] = logf(acc + 1e-18f);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  const int nfr = min(FR, T - t0);
+  for (int i = tid; i < n_mels * FR; i += FW_WARPS * 32) {
+    const int m = i / FR, f = i - m * FR;
+    if (f < nfr) logmel[((long long)b * n_mels + m) * T + t0 + f] = outb[m * (FR + 1) + f];
+  }
+  if (stats) {
+    const int nvalid = min(nfr, len_b - t0);
+    for (int m = tid; m < n_mels; m += FW_WARPS * 32) {
+      float s = 0.f, ss = 0.f;
+      for (int f = 0; f < nvalid; ++f) { const float v = outb[m * (FR + 1) + f]; s += v; ss = fmaf(v, v, ss); }
+      if (nvalid > 0) { atomicAdd(stats + 2 * m, (double)s); atomicAdd(stats + 2 * m + 1, (double)ss); }
+    }
+  }
+}
+
+static size_t logmel1024_smem(int n_mels) {
+  size_t fl = 2 * 1024 + 1024 + (size_t)n_mels * (FR + 1);
+  fl += fl & 1;
+  fl += (size_t)FW_WARPS * 32 * FW_TP * 2;
+  return fl * sizeof(float);
+}
+
 static size_t logmel_smem(bool from_audio, int N, int n_bins, int n_mels, int window_length) {
   size_t fl = 0;
   if (from_audio) fl += 2 * (size_t)N * 2 + (size_t)N;   // bufA, bufB (float2), tw (N/2 float2)
@@ -153,6 +308,16 @@ extern "C" int pbsed_stft_logmel(const float* audio, int B, int S, int shift, in
   if (fft_size < 8 || fft_size > 4096 || (fft_size & (fft_size - 1))) return PBSED_EINVAL;
   if (window_length < 1 || window_length > fft_size) return PBSED_EINVAL;
   const int n_bins = fft_size / 2 + 1;
+  if (fft_size == 1024 && logmel1024_smem(n_mels) <= 200 * 1024) {
+    const size_t sm = logmel1024_smem(n_mels);
+    cudaError_t e = cudaFuncSetAttribute(logmel1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid(cdiv(T, FR), B);
+    logmel1024_kernel<<<grid, FW_WARPS * 32, sm, (cudaStream_t)stream>>>(
+        audio, S, shift, window_length, pad_front, T, window, fbank_lo, fbank_hi, fbank_w, fbank_stride,
+        n_mels, fbank_per_clip, frame_start, seq_len, logmel, stats);
+    return pbsed_after_launch();
+  }
   const size_t smem = logmel_smem(true, fft_size, n_bins, n_mels, window_length);
   if (smem > 200 * 1024) return PBSED_EINVAL;
   cudaError_t e = cudaFuncSetAttribute(logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
