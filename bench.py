@@ -280,7 +280,8 @@ def run_gpu(args):
         out = {
             'metric': 'fbcrnn_train_clips_per_sec', 'value': value, 'unit': '10s-clips/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
+                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate; reduced precision >= bf16 mantissa)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': f'BASELINE configs[1]: FBCRNN shallow (3.49M params) 128-mel, batch {B}/GPU of 10 s / '
                                    '16 kHz clips, K=10, fp32, full train step (GPU STFT+logmel, CNN, fwd+bwd GRU, '
@@ -420,7 +421,8 @@ def run_bicrnn_infer(args):
             'metric': 'bicrnn_inference_clips_per_sec', 'value': v, 'unit': '10s-clips/s', 'frames_per_sec': v * T_FRAMES,
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': float(ms) / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)' if args.precision != 'fp32' else 'f32',
+            'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
+                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': f'BASELINE configs[3]: strong_label tag-conditioned BiCRNN inference, batch {B}/GPU of '
                                    '10 s / 16 kHz clips, eval mode, raw audio -> frame scores -> sequence mask + '
@@ -441,7 +443,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='fbcrnn_train', choices=['fbcrnn_train', 'bicrnn_infer'],
                     help='fbcrnn_train = BASELINE configs[1] (the headline); bicrnn_infer = configs[3]')

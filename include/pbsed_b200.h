@@ -122,7 +122,8 @@ typedef struct {
   long long w_tap_stride, w_sn, w_sc;
   int in_stride;     /* row stride of `in` in floats  (0 -> Cin;  lets a GRU direction read its half of a (B,T,2H) map) */
   int out_stride;    /* row stride of `out` / `dout` / `ep_src` in floats (0 -> Cout) */
-  int precision;     /* 0 = exact fp32 FFMA; 1 = 3xTF32 tcgen05 (fp32-equivalent split) */
+  int precision;     /* 0 = exact fp32 FFMA; 1 = 3xTF32 tcgen05 (fp32-equivalent split);
+                        3 = one TF32 tcgen05 pass, fp32 accumulation (reduced precision, >= bf16 mantissa) */
   int no_input_mask; /* 1: seq_len does NOT zero the loaded operand (a bare conv reads its input unmasked,
                         the reference masks inside Normalization only); seq_len still masks the fused
                         statistics / epilogue */

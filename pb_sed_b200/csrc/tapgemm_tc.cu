@@ -7,6 +7,9 @@
 //                acc += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (kind::tf32, fp32 accumulation in TMEM)
 //                => fp32-equivalent accuracy (one TF32 pass misses the 1e-3
 //                frame-logit bar by 40x, the split meets it with 30x margin)
+//   precision 3: ONE TF32 pass (operands rounded to nearest TF32, fp32 accumulation) -- the
+//                reduced-precision mode for the BASELINE "bf16" configurations: 10 mantissa bits
+//                (> bf16's 7) at a third of the tensor work; the lo images are neither built nor read.
 //
 // CTA = one (b, fo) row group x up to 512 frames (4 row tiles of 128) x a slice of N <= 128 output
 // channels.  Accumulators: 4 x N fp32 columns of TMEM.  Warp roles:
@@ -45,7 +48,13 @@ struct TcParams {
   int n_slices, nkb, ntaps;
   int ngroups;           // taps grouped by df
   int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
+  int single;            // 1: one TF32 pass (precision 3), no lo parts
 };
+
+// round-to-nearest TF32 (single-pass mode; the split mode truncates because hi + lo is exact either way)
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u);
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +138,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
 __global__ void __launch_bounds__(256)
 wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
              int ntaps, int Cin, int Cout, int N, float* __restrict__ img, double* __restrict__ rep,
-             int rep_count) {
+             int rep_count, int single) {
   const int nkb = Cin / KB, n_slices = Cout / N;
   const long long total = (long long)n_slices * ntaps * nkb * KCH * N * 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -144,7 +153,7 @@ wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn
     const int sl = (int)(q / ntaps);
     const int cin = kb * KB + c * 4 + e, cout = sl * N + n;
     const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)cout * w_sn + (long long)cin * w_sc);
-    const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const float hi = single ? tf32_rn(w) : __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     const long long blob = ((long long)(sl * ntaps + tap) * nkb + kb) * (2LL * KCH * N * 4);
     const long long off = ((long long)c * N + n) * 4 + e;
     img[blob + off] = hi;
@@ -282,8 +291,12 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
         const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         const uint32_t o = (uint32_t)(c * RMAX + r) * 16;
-        *reinterpret_cast<float4*>(hi_base + o) = h;
-        *reinterpret_cast<float4*>(lo_base + o) = l;
+        if (p.single) {
+          *reinterpret_cast<float4*>(hi_base + o) = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+        } else {
+          *reinterpret_cast<float4*>(hi_base + o) = h;
+          *reinterpret_cast<float4*>(lo_base + o) = l;
+        }
       }
       fence_async_smem();
       mbar_arrive(&ctl->a_full[slot]);
@@ -418,8 +431,10 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
                 const uint64_t dah = make_desc(a_hi + ao, a_lbo, 128), dal = make_desc(a_lo + ao, a_lbo, 128);
                 const uint64_t dbh = make_desc(b_hi + bo, b_lbo, 128), dbl = make_desc(b_lo + bo, b_lbo, 128);
                 mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
-                mma_tf32(d, dal, dbh, idesc, 1u);
-                mma_tf32(d, dah, dbl, idesc, 1u);
+                if (!p.single) {
+                  mma_tf32(d, dal, dbh, idesc, 1u);
+                  mma_tf32(d, dah, dbl, idesc, 1u);
+                }
               }
             }
             first = false;
@@ -444,8 +459,9 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
             const int bslot = bt % NBUF;
             mbar_wait(&ctl->b_empty[bslot], ((bt / NBUF) & 1) ^ 1);
             const long long blob = ((long long)(slice * p.ntaps + p.g_tap[g][j]) * p.nkb + kb) * (long long)(B_STAGE / 4);
-            mbar_expect_tx(&ctl->b_full[bslot], B_STAGE);
-            bulk_g2s(b_smem + bslot * B_STAGE, img + blob, B_STAGE, &ctl->b_full[bslot]);
+            const uint32_t nbytes = p.single ? B_PART : B_STAGE;     // the hi image leads every blob
+            mbar_expect_tx(&ctl->b_full[bslot], nbytes);
+            bulk_g2s(b_smem + bslot * B_STAGE, img + blob, nbytes, &ctl->b_full[bslot]);
             ++bt;
           }
         }
@@ -487,6 +503,7 @@ struct WgParams {
   int ngroups;
   int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
   int row_splits;
+  int single;            // 1: one TF32 pass (precision 3)
 };
 
 struct __align__(16) WgCtl {
@@ -494,7 +511,12 @@ struct __align__(16) WgCtl {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t o, float a, float b, float c, float d) {
+__device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t o, float a, float b, float c, float d,
+                                            int single) {
+  if (single) {
+    *reinterpret_cast<float4*>(hi + o) = make_float4(tf32_rn(a), tf32_rn(b), tf32_rn(c), tf32_rn(d));
+    return;
+  }
   float4 h;
   h.x = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
   h.y = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
@@ -624,10 +646,10 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
           if (j >= WG_ZCH) break;
           const float4* v = zv[k];
           const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
-          split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x);
-          split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y);
-          split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z);
-          split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w);
+          split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+          split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+          split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+          split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
           if (do_bias) {
             bsum.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); bsum.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
             bsum.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); bsum.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
@@ -652,10 +674,10 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
             }
           }
           const uint32_t o = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
-          split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x);
-          split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y);
-          split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z);
-          split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w);
+          split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+          split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+          split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+          split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
         }
         fence_async_smem();
         mbar_arrive(&ctl->full[slot]);
@@ -719,8 +741,10 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
               const uint64_t dzh = make_desc(z_hi + zo, Z_LBO, 128), dzl = make_desc(z_lo + zo, Z_LBO, 128);
               const uint64_t dah = make_desc(a_hi + ao, A_LBO, 128), dal = make_desc(a_lo + ao, A_LBO, 128);
               mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
-              mma_tf32(d, dzl, dah, idesc, 1u);
-              mma_tf32(d, dzh, dal, idesc, 1u);
+              if (!p.single) {
+                mma_tf32(d, dzl, dah, idesc, 1u);
+                mma_tf32(d, dzh, dal, idesc, 1u);
+              }
             }
           }
           mma_commit(&ctl->empty[slot]);
@@ -770,7 +794,7 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
                         cudaStream_t st, int* handled) {
   *handled = 0;
   if (out_stats && ep_sums) return 0;
-  if (d->precision != 1 || !workspace || !tc_eligible(d)) return 0;
+  if ((d->precision != 1 && d->precision != 3) || !workspace || !tc_eligible(d)) return 0;
   if (ws_bytes < pbsed_tapgemm_workspace_bytes(d)) return PBSED_EWORKSPACE;
   if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale |
         (uintptr_t)shift | (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift |
@@ -785,6 +809,7 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   p.n_slices = d->Cout / p.N;
   p.nkb = d->Cin / KB;
   p.ntaps = d->ntaps;
+  p.single = d->precision == 3;
   // group taps by df
   for (int i = 0; i < d->ntaps; ++i) {
     int g = 0;
@@ -802,7 +827,7 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img,
-                                         rep, want_sums ? STAT_REP * stat_n * 2 : 0);
+                                         rep, want_sums ? STAT_REP * stat_n * 2 : 0, p.single);
     int rc = pbsed_after_launch();
     if (rc) return rc;
   }
@@ -845,7 +870,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
                               const float* shift, const int* seq_len, const float* dout,
                               int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (d->precision != 1 || !tc_eligible(d)) return 0;
+  if ((d->precision != 1 && d->precision != 3) || !tc_eligible(d)) return 0;
   if (d->Cin > NSLICE && d->Cin % NSLICE) return 0;
   // measured crossover (B200, B=32): with <= 32 channels on a side the 128-lane MMA is mostly padding
   // and the FFMA kernel wins; see DESIGN.md
@@ -857,6 +882,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   p.in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
   p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
   p.w_tap_stride = d->w_tap_stride; p.w_sn = d->w_sn; p.w_sc = d->w_sc;
+  p.single = d->precision == 3;
   p.Ms = d->Cout < NSLICE ? d->Cout : NSLICE;
   p.m_slices = d->Cout / p.Ms;
   p.Nc = d->Cin < NSLICE ? d->Cin : NSLICE;

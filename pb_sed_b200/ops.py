@@ -19,12 +19,15 @@ from ._lib import TapGemmDesc, call
 
 import os
 
-PRECISION = {'fp32': 0, 'tf32x3': 1, 'bf16': 2}
+PRECISION = {'fp32': 0, 'tf32x3': 1, 'tf32': 3}
 _default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'tf32x3')]
 
 
 def set_default_precision(p):
-    """'fp32' (exact FFMA), 'tf32x3' (tcgen05 split-TF32), 'bf16' (tcgen05) for the tap-GEMMs."""
+    """precision of the tap-GEMMs: 'fp32' (exact FFMA), 'tf32x3' (tcgen05, 3-pass split TF32 =
+    fp32-equivalent, the default) or 'tf32' (tcgen05, ONE TF32 pass with fp32 accumulation: the
+    reduced-precision mode offered for the BASELINE "bf16" configurations -- 10 mantissa bits, i.e.
+    at least bf16's 7, at a third of the tensor work)."""
     global _default_precision
     _default_precision = PRECISION[p] if isinstance(p, str) else int(p)
 

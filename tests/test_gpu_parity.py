@@ -323,6 +323,41 @@ def test_full_size_fbcrnn_logits_and_train_step_vs_oracle():
     assert abs(float(gnorm) - float(ref_gnorm)) < 1e-3 * float(ref_gnorm)
 
 
+def test_full_size_fbcrnn_single_pass_tf32_mode():
+    """precision 'tf32' (one TF32 pass; the mode offered for BASELINE's bf16 configurations) on the
+    full-size FBCRNN: stated tolerance frame-logit max|delta| <= 0.1 (|logit| ~ 6), loss 2 %,
+    gradient norm 5 % against the fp32 CPU oracle."""
+    from pb_sed_b200 import config, train, ops
+    from pb_sed_b200.models import weak_label
+    ora = OM.build_fbcrnn(seed=0)
+    model = weak_label.CRNN.from_config_dict(config.fbcrnn_config())
+    model.load_state_dict(ora.state_dict())
+    model.to(DEV)
+    model.emit_buffers = False
+    batch = OM.synthetic_batch(2, seed=11)
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'stft'}
+    opt = train.Adam(model, lr=5e-4)
+    model.train()
+    ops.set_default_precision('tf32')
+    try:
+        out = model(dict(gb))
+        loss = model.review(gb, out)['loss']
+        loss.backward()
+        z_fwd = model._z_fwd.detach().cpu()
+        gnorm = opt.step()
+    finally:
+        ops.set_default_precision('tf32x3')
+    cb = {k: v for k, v in batch.items() if k != 'audio_data'}
+    ora.train()
+    zr_fwd, *_ = ora.logits(cb)
+    ora2 = OM.build_fbcrnn(seed=0)
+    ref_loss, ref_gnorm, _ = OM.train_step(ora2, OM.make_adam(ora2), cb)
+    d = maxdiff(z_fwd.transpose(1, 2), zr_fwd)
+    assert 1e-3 < d < 0.1, d                                   # really reduced precision, within the stated bound
+    assert abs(float(loss) - float(ref_loss)) < 2e-2 * float(ref_loss)
+    assert abs(float(gnorm) - float(ref_gnorm)) < 5e-2 * float(ref_gnorm)
+
+
 def test_graphed_train_step_equals_eager():
     from pb_sed_b200 import train
     ora, m1 = tiny_pair(seed=2)

@@ -147,3 +147,38 @@ def test_tc_wgrad_flatten_and_strided_input(built_lib):
                           x_ptr=ctypes.c_void_p(h.data_ptr() + 4 * H))
         res.append((dW, db))
     assert reldiff(res[1][0], res[0][0]) < 5e-5 and reldiff(res[1][1], res[0][1]) < 5e-5
+
+
+# ------------------------------------------------------------------ precision 3: one TF32 pass
+@pytest.mark.parametrize('B,F,T,Cin,Cout,taps', [
+    (2, 4, 500, 32, 64, TAPS_3x3),
+    (1, 2, 260, 128, 256, TAPS_3x3),
+    (3, 1, 500, 256, 768, TAPS_1x1),
+])
+def test_single_pass_tf32_forward_and_wgrad(built_lib, B, F, T, Cin, Cout, taps):
+    """reduced-precision mode (BASELINE 'bf16' configurations): operands rounded to nearest TF32
+    (unit round-off 2^-11), fp32 accumulation.  Tolerance: 3e-3 of the output range -- and it must be
+    measurably different from the fp32-equivalent split, i.e. the single pass is really what ran."""
+    from pb_sed_b200 import ops
+    torch.manual_seed(Cin + T)
+    x = torch.randn(B, F, T, Cin, device=DEV)
+    W = torch.randn(len(taps), Cout, Cin, device=DEV) / np.sqrt(Cin * len(taps))
+    bias = torch.randn(Cout, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    dims = (B, F, F, T, Cin, Cout)
+    ref = run(0, x, W, bias, dims, taps, scale=scale, shift=shift, relu=True)
+    out = run(3, x, W, bias, dims, taps, scale=scale, shift=shift, relu=True)
+    err = reldiff(out, ref)
+    assert 2e-5 < err < 3e-3, err
+    dz = torch.randn(B, F, T, Cout, device=DEV)
+    res = []
+    for prec in (0, 3):
+        desc = ops.make_desc(B, F, F, T, Cin, Cout, taps, relu=True, precision=prec)
+        dW = torch.zeros(len(taps), Cout, Cin, device=DEV)
+        db = torch.zeros(Cout, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, None, mask_out=False)
+        res.append((dW, db))
+    # (narrow layers route the weight gradient to the exact FFMA kernel in every mode: no lower bound here)
+    assert reldiff(res[1][0], res[0][0]) < 3e-3
+    assert reldiff(res[1][1], res[0][1]) < 5e-5          # the bias gradient is summed in fp32 either way
