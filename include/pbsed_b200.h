@@ -174,9 +174,11 @@ int pbsed_norm_finalize(const double* stats, double count, int nch,
                         const float* gamma, const float* beta, float eps, float momentum, int training,
                         float* running_mean, float* running_power, float* num_tracked,
                         float* scale, float* shift, float* save_mean, float* save_rstd, void* stream);
-/* frequency max-pool by `pool` (rows (B,F,T,C) -> (B,F/pool,T,C)); idx (uint8) = argmax offset */
+/* frequency max-pool by `pool` (rows (B,F,T,C) -> (B,F/pool,T,C)); idx (uint8) = argmax offset.
+ * out_stats (nullable, double[C][2]): += per-channel sum / sum of squares of the POOLED map over frames
+ * t < seq_len[b] -- the next layer's batch statistics, fused into the pooling pass. */
 int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool,
-                    float* y, uint8_t* idx, void* stream);
+                    float* y, uint8_t* idx, const int* seq_len, double* out_stats, void* stream);
 int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C, int pool,
                         float* dx, void* stream);
 /* batch-norm backward, two passes.  g = gradient w.r.t. the normalised+affine output (already

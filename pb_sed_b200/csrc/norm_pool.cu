@@ -382,11 +382,18 @@ maxpool_f_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ i
   }
 }
 
-// pool == 2, C % 4 == 0: float4 in, float4 out, uchar4 argmax
+// pool == 2, C % 4 == 0: float4 in, float4 out, uchar4 argmax.  STATS: also accumulate the per-channel
+// sum / sum of squares of the POOLED map over valid frames (the next layer's batch statistics), which
+// saves that layer a full pass over the map.  The grid stride is a multiple of C/4, so a thread keeps
+// the same channel quad for its whole loop and the sums live in registers until the end.
+template <bool STATS>
 __global__ void __launch_bounds__(256)
 maxpool2_f4_kernel(const float4* __restrict__ x, int Fo, long long TC4, float4* __restrict__ y,
-                   uchar4* __restrict__ idx, long long total4) {
+                   uchar4* __restrict__ idx, long long total4, int C4, const int* __restrict__ seq_len,
+                   double* __restrict__ stats) {
+  __shared__ float red[2][1024];
   const long long stride = (long long)gridDim.x * blockDim.x;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     const long long tc = i % TC4, gq = i / TC4;         // gq = b * Fo + fo
     const float4 a = __ldg(x + (2 * gq) * TC4 + tc), c = __ldg(x + (2 * gq + 1) * TC4 + tc);
@@ -397,6 +404,29 @@ maxpool2_f4_kernel(const float4* __restrict__ x, int Fo, long long TC4, float4* 
     k.w = (c.w > a.w || c.w != c.w) ? 1 : 0; r.w = k.w ? c.w : a.w;
     y[i] = r;
     if (idx) idx[i] = k;
+    if (STATS) {
+      const int t = (int)(tc / C4);
+      const int b = (int)(gq / Fo);
+      if (!seq_len || t < __ldg(seq_len + b)) {
+        s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
+        ss.x = fmaf(r.x, r.x, ss.x); ss.y = fmaf(r.y, r.y, ss.y); ss.z = fmaf(r.z, r.z, ss.z); ss.w = fmaf(r.w, r.w, ss.w);
+      }
+    }
+  }
+  if (STATS) {
+    const int C = 4 * C4;
+    for (int j = threadIdx.x; j < C; j += 256) { red[0][j] = 0.f; red[1][j] = 0.f; }
+    __syncthreads();
+    const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % C4);
+    atomicAdd(&red[0][4 * q + 0], s.x); atomicAdd(&red[0][4 * q + 1], s.y);
+    atomicAdd(&red[0][4 * q + 2], s.z); atomicAdd(&red[0][4 * q + 3], s.w);
+    atomicAdd(&red[1][4 * q + 0], ss.x); atomicAdd(&red[1][4 * q + 1], ss.y);
+    atomicAdd(&red[1][4 * q + 2], ss.z); atomicAdd(&red[1][4 * q + 3], ss.w);
+    __syncthreads();
+    for (int j = threadIdx.x; j < C; j += 256) {
+      atomicAdd(stats + 2 * j, (double)red[0][j]);
+      atomicAdd(stats + 2 * j + 1, (double)red[1][j]);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
@@ -426,17 +456,27 @@ static int ew_blocks(long long total) {
 }
 
 extern "C" int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool, float* y,
-                               uint8_t* idx, void* stream) {
+                               uint8_t* idx, const int* seq_len, double* out_stats, void* stream) {
   if (!x || !y || pool < 1 || pool > 255 || F / pool < 1) return PBSED_EINVAL;
   const long long total = (long long)B * (F / pool) * T * C;
   if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)idx)) & 15) == 0) {
-    maxpool2_f4_kernel<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
-        reinterpret_cast<uchar4*>(idx), total / 4);
-    return pbsed_after_launch();
+    const bool fused = out_stats && C <= 1024 && (256 % (C / 4)) == 0;
+    if (fused)
+      maxpool2_f4_kernel<true><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
+          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, seq_len, out_stats);
+    else
+      maxpool2_f4_kernel<false><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
+          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, nullptr, nullptr);
+    int rc = pbsed_after_launch();
+    if (rc || fused || !out_stats) return rc;
+    return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, stream);
   }
   maxpool_f_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, F, (long long)T * C, pool, y, idx, total);
-  return pbsed_after_launch();
+  int rc = pbsed_after_launch();
+  if (rc || !out_stats) return rc;
+  return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, stream);
 }
 
 extern "C" int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C,

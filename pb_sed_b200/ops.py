@@ -317,7 +317,10 @@ class ConvLayerFn(torch.autograd.Function):
         if pool > 1:
             y = torch.empty((B, F_out // pool, T, Cout), device=x.device)
             idx = torch.empty(y.shape, device=x.device, dtype=torch.uint8)
-            call('pbsed_maxpool_f', _ptr(z), B, F_out, T, Cout, pool, _ptr(y), _ptr(idx), _stream())
+            if cfg.get('want_stats') and not cfg.get('stats_per_f', False):
+                stats_out = _stats_buffer(Cout, x.device)      # statistics of the pooled map, same pass
+            call('pbsed_maxpool_f', _ptr(z), B, F_out, T, Cout, pool, _ptr(y), _ptr(idx), seq.ptr,
+                 _ptr(stats_out), _stream())
         else:
             y = z
         ctx.cfg, ctx.seq, ctx.count = cfg, seq, count
