@@ -572,117 +572,150 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
 
   if (warp < WG_PROD / 32) {
     // ============================== producers ==============================
+    // Software-pipelined over stages with a register ROTATION: a stage's dout registers are refilled with
+    // the NEXT stage's loads as soon as they have been transposed into shared memory, and likewise the
+    // input registers, so global-load latency overlaps the other half of the stage's work and the wait
+    // for the ring slot -- without a second register set (measured: this kernel is producer-latency
+    // bound, a third of the MMAs does not make it faster).
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const int zqi = tid % zq;                      // invariant: WG_PROD % zq == 0
     const int aqi = tid % aq;
-    int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
-      const int tb = u % t_blocks, gq = u / t_blocks;
-      const int fo = gq % p.F_out, b = gq / p.F_out;
-      const int f_src = fo + df;
-      const bool f_ok = f_src >= 0 && f_src < p.F_in;
-      if (!f_ok && !do_bias) continue;
-      const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
-      const int len_out = p.mask_out ? len_b : p.T;
-      const float* zsrc = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
-      const float* asrc = in + ((long long)b * p.F_in + f_src) * p.T * p.in_stride + c0 + aqi * 4;
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (scale && f_ok) {
-        const int aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
-        sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
-        sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+    constexpr int ZT = 2, AT = 3;
+    float4 zv[ZT][4], av[AT][4];
+    const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
+    struct StageCtx { int u, t0, t_end, len_b, len_out, aff; const float* zsrc; const float* asrc; };
+
+    auto advance = [&](StageCtx& s) -> bool {      // next stage with a valid source row (bias-only visits inline)
+      if (s.u >= 0) {
+        s.t0 += WG_KR;
+        if (s.t0 < s.t_end) return true;
       }
-      const int t_end = min(p.T, (tb + 1) * WG_TB);
-      for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR) {
+      for (int u = s.u < 0 ? (int)blockIdx.x : s.u + p.row_splits; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out, b = gq / p.F_out;
+        const int f_src = fo + df;
+        const bool f_ok = f_src >= 0 && f_src < p.F_in;
+        if (!f_ok && !do_bias) continue;
+        const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+        const int len_out = p.mask_out ? len_b : p.T;
+        const float* zsrc = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
         if (!f_ok) {                                 // bias-only visit of a border row group
-          for (int j = tid / zq; j < WG_ZCH; j += WG_PROD / zq)
+          for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR)
+            for (int j = tid / zq; j < WG_ZCH; j += WG_PROD / zq)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int t = t0 + j + 8 * i;
-              if (t < len_out) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
-                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+              for (int i = 0; i < 4; ++i) {
+                const int t = t0 + j + 8 * i;
+                if (t < len_out) {
+                  const float4 v = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
+                  bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+                }
               }
-            }
           continue;
         }
-        const int slot = it % WG_STAGES;
-        uint8_t* z_hi = smem_raw + slot * STAGE;
-        uint8_t* z_lo = z_hi + Z_PART;
-        uint8_t* a_hi = z_lo + Z_PART;
-        uint8_t* a_lo = a_hi + A_PART;
-        // every thread first issues ALL its loads of this stage (<= 2 dout tasks + <= 3 input tasks of
-        // four 16-byte loads each), then transposes 4x4 blocks and stores quad-major K-major chunks
-        constexpr int ZT = 2, AT = 3;
-        float4 zv[ZT][4], av[AT][4];
-        const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
-#pragma unroll
-        for (int k = 0; k < ZT; ++k) {
-          const int j = zj0 + k * zjs;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int t = t0 + j + 8 * i;
-            zv[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < WG_ZCH && t < len_out)
-              zv[k][i] = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < AT; ++k) {
-          const int jj = aj0 + k * ajs;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int t = t0 + jj - 1 + 8 * i;
-            av[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jj < WG_ACH && t >= 0 && t < len_b)
-              av[k][i] = __ldg(reinterpret_cast<const float4*>(asrc + (long long)t * p.in_stride));
-          }
-        }
-        // only the stores are gated by the ring slot: the loads above are already in flight
-        mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);
-#pragma unroll
-        for (int k = 0; k < ZT; ++k) {
-          const int j = zj0 + k * zjs;
-          if (j >= WG_ZCH) break;
-          const float4* v = zv[k];
-          const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
-          split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
-          split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
-          split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
-          split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
-          if (do_bias) {
-            bsum.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); bsum.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
-            bsum.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); bsum.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < AT; ++k) {
-          const int jj = aj0 + k * ajs;
-          if (jj >= WG_ACH) break;
-          float4* v = av[k];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int t = t0 + jj - 1 + 8 * i;
-            if (t >= 0 && t < len_b) {
-              float4 x = v[i];
-              if (scale) {
-                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
-                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-              }
-              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              v[i] = x;
-            }
-          }
-          const uint32_t o = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
-          split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
-          split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
-          split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
-          split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
-        }
-        fence_async_smem();
-        mbar_arrive(&ctl->full[slot]);
-        ++it;
+        s.u = u; s.t0 = tb * WG_TB; s.t_end = t_end; s.len_b = len_b; s.len_out = len_out;
+        s.zsrc = zsrc;
+        s.asrc = in + ((long long)b * p.F_in + f_src) * p.T * p.in_stride + c0 + aqi * 4;
+        s.aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
+        return true;
       }
+      s.u = total_units;
+      return false;
+    };
+    auto load_z = [&](const StageCtx& s) {
+#pragma unroll
+      for (int k = 0; k < ZT; ++k) {
+        const int j = zj0 + k * zjs;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = s.t0 + j + 8 * i;
+          zv[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < WG_ZCH && t < s.len_out)
+            zv[k][i] = __ldg(reinterpret_cast<const float4*>(s.zsrc + (long long)t * p.out_stride));
+        }
+      }
+    };
+    auto load_a = [&](const StageCtx& s) {
+#pragma unroll
+      for (int k = 0; k < AT; ++k) {
+        const int jj = aj0 + k * ajs;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = s.t0 + jj - 1 + 8 * i;
+          av[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (jj < WG_ACH && t >= 0 && t < s.len_b)
+            av[k][i] = __ldg(reinterpret_cast<const float4*>(s.asrc + (long long)t * p.in_stride));
+        }
+      }
+    };
+
+    int it = 0;
+    StageCtx cur;
+    cur.u = -1; cur.t0 = 0; cur.t_end = 0;
+    bool have = advance(cur);
+    if (have) { load_z(cur); load_a(cur); }
+    while (have) {
+      const int slot = it % WG_STAGES;
+      uint8_t* z_hi = smem_raw + slot * STAGE;
+      uint8_t* z_lo = z_hi + Z_PART;
+      uint8_t* a_hi = z_lo + Z_PART;
+      uint8_t* a_lo = a_hi + A_PART;
+      // only the stores are gated by the ring slot: this stage's loads have been in flight since the
+      // previous iteration
+      mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);
+#pragma unroll
+      for (int k = 0; k < ZT; ++k) {
+        const int j = zj0 + k * zjs;
+        if (j >= WG_ZCH) break;
+        const float4* v = zv[k];
+        const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
+        split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+        split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+        split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+        split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
+        if (do_bias) {
+          bsum.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); bsum.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+          bsum.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); bsum.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
+        }
+      }
+      StageCtx nxt = cur;
+      const bool have_n = advance(nxt);
+      if (have_n) load_z(nxt);                       // dout registers are free again: refill them
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (scale) {
+        sc = __ldg(reinterpret_cast<const float4*>(scale + cur.aff));
+        sh = __ldg(reinterpret_cast<const float4*>(shift + cur.aff));
+      }
+#pragma unroll
+      for (int k = 0; k < AT; ++k) {
+        const int jj = aj0 + k * ajs;
+        if (jj >= WG_ACH) break;
+        float4* v = av[k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = cur.t0 + jj - 1 + 8 * i;
+          if (t >= 0 && t < cur.len_b) {
+            float4 x = v[i];
+            if (scale) {
+              x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+              x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+            }
+            if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            v[i] = x;
+          }
+        }
+        const uint32_t o = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
+        split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+        split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+        split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+        split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
+      }
+      if (have_n) load_a(nxt);                       // input registers are free again
+      fence_async_smem();
+      mbar_arrive(&ctl->full[slot]);
+      ++it;
+      cur = nxt;
+      have = have_n;
     }
     if (do_bias) {
       float* db = dbias + m0 + zqi * 4;
