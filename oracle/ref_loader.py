@@ -129,3 +129,18 @@ def load_filters():
     inf = _exec('pb_sed.models.base.inference', 'pb_sed/models/base/inference.py')
     _loaded.update(filters=filt, inference=inf)
     return filt, inf
+
+
+def load_segment():
+    """the REAL ``pb_sed/utils/segment.py`` (``merge_segments`` is pure numpy; ``segment_batch`` needs
+    padertorch's Segmenter, which is stubbed out and therefore NOT usable through this loader)."""
+    if 'segment' in _loaded:
+        return _loaded['segment']
+    assert reference_available(), REFERENCE_ROOT
+    for name in ('padertorch', 'padertorch.data'):
+        if name not in sys.modules:
+            _stub(name)
+    _stub('padertorch.data.segment', Segmenter=None)
+    seg = _exec('pb_sed_ref_utils_segment', 'pb_sed/utils/segment.py')
+    _loaded['segment'] = seg
+    return seg

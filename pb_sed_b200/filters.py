@@ -117,7 +117,7 @@ def tag_mask_(scores, tags, apply_mask):
     s4 = scores[:, None] if squeeze else scores
     assert s4.is_contiguous() and s4.dtype == torch.float32
     B, N, K, T = s4.shape
-    ap = np.ascontiguousarray(np.broadcast_to(ap if ap.ndim == 2 else ap.reshape(1, -1) if ap.ndim == 1 else ap.reshape(1, 1), (N, K)))
+    ap = np.broadcast_to(ap if ap.ndim == 2 else ap.reshape(1, -1) if ap.ndim == 1 else ap.reshape(1, 1), (N, K)).copy()
     ap_dev = torch.from_numpy(ap).to(scores.device)
     tg = _f32c(tags.to(scores.device))
     assert tg.shape == (B, K), tg.shape
