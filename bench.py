@@ -28,8 +28,9 @@ FLOP_PER_CLIP_TRAIN = 35.26e9          # fwd 11.75 GFLOP, fwd+bwd 3
 CPU_SAMPLE_BATCH = 4
 
 
-def synthetic_clips(batch, seed):
+def synthetic_clips(batch, seed, num_events=None):
     """low-passed noise + gated sinusoid events, peak normalised; float32 (B,1,S)."""
+    NUM_EVENTS = num_events or globals()['NUM_EVENTS']
     rng = np.random.RandomState(seed)
     x = rng.randn(batch, NUM_SAMPLES)
     spec = np.fft.rfft(x, axis=-1)
@@ -209,14 +210,15 @@ def run_gpu(args):
     ops.set_default_precision(args.precision)
     B = args.batch
     torch.manual_seed(0)
-    model = weak_label.CRNN.from_config_dict(config.fbcrnn_config(num_events=NUM_EVENTS)).to(dev)
+    model = weak_label.CRNN.from_config_dict(config.fbcrnn_config(
+        num_events=args.num_events, strong_fwd_bwd_loss_weight=args.strong_weight)).to(dev)
     model.emit_buffers = False
-    opt = train.Adam(model, lr=5e-4, gradient_clipping=1e10, sync_stats=args.sync_stats)
+    opt = train.Adam(model, lr=args.lr, gradient_clipping=args.grad_clip, sync_stats=args.sync_stats)
 
     n_sets = 3
     host = []
     for i in range(n_sets):
-        audio, weak, boundary = synthetic_clips(B, 1234 + 1000 * rank + i)
+        audio, weak, boundary = synthetic_clips(B, 1234 + 1000 * rank + i, args.num_events)
         host.append({'audio_data': torch.from_numpy(audio).pin_memory(),
                      'weak_targets': torch.from_numpy(weak).pin_memory(),
                      'boundary_targets': torch.from_numpy(boundary).pin_memory()})
@@ -283,9 +285,12 @@ def run_gpu(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
                       'tf32': 'tf32 single pass (tcgen05, fp32 accumulate; reduced precision >= bf16 mantissa)'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': f'BASELINE configs[1]: FBCRNN shallow (3.49M params) 128-mel, batch {B}/GPU of 10 s / '
-                                   '16 kHz clips, K=10, fp32, full train step (GPU STFT+logmel, CNN, fwd+bwd GRU, '
-                                   'pb_sed loss, backward, clip+Adam)',
+            'config': {'workload': (f'BASELINE configs[1]: FBCRNN shallow (3.49M params) 128-mel, batch {B}/GPU of 10 s / '
+                                    '16 kHz clips, K=10, fp32, full train step (GPU STFT+logmel, CNN, fwd+bwd GRU, '
+                                    'pb_sed loss, backward, clip+Adam)') if (args.num_events == 10 and B == 32) else
+                                   (f'FBCRNN shallow 128-mel, batch {B}/GPU of 10 s / 16 kHz clips, K={args.num_events}, '
+                                    f'strong_fwd_bwd_loss_weight={args.strong_weight}, gradient_clipping={args.grad_clip}, '
+                                    f'lr={args.lr}, full train step'),
                        'global_batch': B * world, 'parallelism': f'dp{world}', 'precision': args.precision,
                        'sync_stats': args.sync_stats if world > 1 else 'n/a (1 GPU)',
                        'l2': f'{n_sets} distinct input batches rotate; per-step activation working set (several GB) '
@@ -445,6 +450,10 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--num-events', type=int, default=NUM_EVENTS, help='K (527 = AudioSet, training.py:128)')
+    ap.add_argument('--strong-weight', type=float, default=1., help='strong_fwd_bwd_loss_weight (0 for AudioSet, :151)')
+    ap.add_argument('--grad-clip', type=float, default=1e10, help='gradient_clipping (0.1 for AudioSet, :150)')
+    ap.add_argument('--lr', type=float, default=5e-4)
     ap.add_argument('--workload', default='fbcrnn_train', choices=['fbcrnn_train', 'bicrnn_infer'],
                     help='fbcrnn_train = BASELINE configs[1] (the headline); bicrnn_infer = configs[3]')
     ap.add_argument('--sync-stats', default='none', choices=['none', 'exact'],

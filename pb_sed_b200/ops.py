@@ -352,7 +352,10 @@ class ConvLayerFn(torch.autograd.Function):
             with _WgradStream(x, dz, scale, shift):
                 tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq if cfg['norm'] else None, mask_out=False)
         dx = dg_ret = dbe_ret = None
-        if ctx.needs_input_grad[0]:
+        # the data-gradient pass is also what yields this layer's OWN norm gradients (dgamma, dbeta): it must
+        # run when only they are wanted (input produced by frozen layers, training.py:343-350)
+        norm_grads = cfg['norm'] and cfg['training'] and g_p is not None and g_p.requires_grad
+        if ctx.needs_input_grad[0] or norm_grads:
             rtaps = [(-df, -dt) for df, dt in cfg['taps']]
             ddesc = make_desc(B, F_out, F_in, T, Cout, Cin, rtaps, per_f=per_f, transpose_w=True)
             train_norm = cfg['norm'] and cfg['training']
@@ -394,6 +397,8 @@ class ConvLayerFn(torch.autograd.Function):
                 dx = g * sc
             else:
                 dx = g
+            if not ctx.needs_input_grad[0]:
+                dx = None
         return dx, dW_ret, db_ret, dg_ret, dbe_ret, None, None, None, None, None, None
 
 

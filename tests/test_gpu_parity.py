@@ -480,3 +480,46 @@ def test_augmented_train_step_is_graph_capturable():
         loss, _ = step(gb)
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and len(set(losses)) == 3, losses
+
+
+# ------------------------------------------------------------------ model options (weak_label/crnn.py:36-55, training.py:343-350)
+def test_slat_label_smoothing_and_class_weights_through_the_model():
+    """slat=True builds the boundary targets from the weak ones (crnn.py:130-131); label smoothing and
+    class weights ride through CRNN.loss."""
+    cw = (np.arange(10) / 10. + .5).tolist()
+    kw = dict(slat=True, label_smoothing=.05, class_weights=cw)
+    ora, prod = tiny_pair(seed=4, **kw)
+    batch = OM.synthetic_batch(4, num_samples=645, stft_kwargs=TINY_STFT, seq_len=[41, 40, 33, 17], seed=4)
+    batch.pop('boundary_targets')
+    batch['weak_targets'][2, 1] = .5
+    ora.train(); prod.train()
+    cb = {k: v for k, v in batch.items() if k != 'audio_data'}
+    ref = ora.review(cb, ora(dict(cb)))['loss']
+    ref.backward()
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in cb.items()}
+    loss = prod.review(gb, prod(dict(gb)))['loss']
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-4
+    g = ref_layout_grads(prod)
+    for k, p in ora.named_parameters():
+        assert maxdiff(g[k], p.grad) < 5e-4 * max(1., float(p.grad.abs().max())), k
+
+
+def test_freeze_stops_gradients_of_the_first_layers():
+    """cnn_2d.freeze(n) / cnn_1d.freeze() of the fine-tuning recipe (training.py:343-350): frozen layers get
+    no gradient, the rest match the unfrozen run."""
+    ora, prod = tiny_pair(seed=5)
+    _, ref = tiny_pair(seed=5)
+    prod.cnn.cnn_2d.freeze(2)
+    batch = OM.synthetic_batch(4, num_samples=645, stft_kwargs=TINY_STFT, seed=5)
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'audio_data'}
+    for m in (prod, ref):
+        m.train()
+        m.review(gb, m(dict(gb)))['loss'].backward()
+    for (n, p), (_, q) in zip(prod.named_parameters(), ref.named_parameters()):
+        frozen = n.startswith('cnn.cnn_2d.convs.0') or n.startswith('cnn.cnn_2d.convs.1') or \
+            n.startswith('cnn.cnn_2d.norms.1')
+        if frozen:
+            assert not p.requires_grad and p.grad is None, n
+        else:
+            assert p.grad is not None and maxdiff(p.grad, q.grad) < 1e-5 * max(1., float(q.grad.abs().max())), n
