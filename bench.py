@@ -319,6 +319,7 @@ def run_gpu(args):
             'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_sus, 'unit': 'TFLOP/s',
             'frac': (achieved / tf_sus) if achieved else None, 'traffic': traffic, 'traffic_source': traffic_src,
             'executed_tensor_tflops': (3. * achieved if (achieved and args.precision == 'tf32x3') else achieved),
+            'executed_frac_of_tf32_peak': ((3. if args.precision == 'tf32x3' else 1.) * achieved / (tf_sus / 2.)) if achieved else None,
             'peak_source': f'{which} bf16 dense sustained (MEASURED_PEAKS.json); the fp32 config runs '
                            f'{args.precision} arithmetic, TF32 nominal peak is half of bf16',
             'avg_launch_ms': r['ms'] / r['calls'], 'launches_per_step': r['calls'],
