@@ -1,0 +1,112 @@
+"""Batch assembly and the host->device input pipeline.
+
+Mirrors what the reference does between ``Transform`` and the model:
+``pb_sed/data_preparation/fetcher.py:36-51`` (examples of a bucket sorted by ``seq_len`` descending,
+then padertorch ``Collate()``: arrays zero-padded to the longest example and stacked, everything else
+gathered in lists) and ``Model.example_to_device`` (``pb_sed/models/base/inference.py:130``).  The
+differences are the ones the B200 path wants: batches land in PINNED host memory, raw audio
+(``Transform(pop_audio_data=False)``, transform.py:17,126-127) can replace the 3.2x larger ``stft``
+(20.5 MB instead of 65.7 MB per batch of 32), and ``DeviceLoader`` copies batch i+1
+on a copy stream while batch i computes.
+"""
+import numpy as np
+import torch
+
+from .modules import stft_num_frames
+
+_PAD_LAST = ('boundary_targets', 'strong_targets')     # (K, T): time is the last axis
+_STACK = ('weak_targets', 'tag_condition')
+
+
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def collate(examples, keep_stft=True, stft_kwargs=None):
+    """list of example dicts (transform.py:65-72,115,124) -> batch dict of pinned tensors.
+
+    ``stft`` (1, T, F, 2) and ``audio_data`` (1, S) are zero-padded along time / samples;
+    ``boundary_targets`` / ``strong_targets`` (K, T) along T; ``seq_len`` (frames) is taken from the
+    example, or derived from the number of samples with the reference STFT geometry when only audio is
+    there.  Examples are sorted by ``seq_len`` descending (fetcher.py:49-50: the GRU packs them)."""
+    assert len(examples) > 0
+    kw = dict(shift=320, window_length=960, fading='half', pad=True)
+    kw.update({k: v for k, v in (stft_kwargs or {}).items() if k in kw})
+    ex = []
+    for e in examples:
+        e = dict(e)
+        if 'seq_len' not in e:
+            e['seq_len'] = (e['stft'].shape[1] if 'stft' in e else
+                            stft_num_frames(np.asarray(e['audio_data']).shape[-1], **kw))
+        ex.append(e)
+    ex.sort(key=lambda e: -int(e['seq_len']))
+    batch = {}
+    for key in ex[0]:
+        vals = [e[key] for e in ex]
+        if key == 'stft':
+            if not keep_stft and 'audio_data' in ex[0]:
+                continue
+            T = max(np.asarray(v).shape[1] for v in vals)
+            out = torch.zeros((len(vals),) + tuple(np.asarray(vals[0]).shape[:1]) + (T,) + tuple(np.asarray(vals[0]).shape[2:]))
+            for i, v in enumerate(vals):
+                v = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+                out[i, :, :v.shape[1]] = v
+            batch[key] = _pin(out)
+        elif key == 'audio_data':
+            S = max(np.asarray(v).shape[-1] for v in vals)
+            out = torch.zeros((len(vals), 1, S))
+            for i, v in enumerate(vals):
+                v = torch.as_tensor(np.asarray(v), dtype=torch.float32).reshape(1, -1)
+                out[i, :, :v.shape[-1]] = v
+            batch[key] = _pin(out)
+        elif key in _PAD_LAST:
+            T = max(np.asarray(v).shape[-1] for v in vals)
+            out = torch.zeros((len(vals), np.asarray(vals[0]).shape[0], T))
+            for i, v in enumerate(vals):
+                v = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+                out[i, :, :v.shape[-1]] = v
+            batch[key] = _pin(out)
+        elif key in _STACK:
+            batch[key] = _pin(torch.as_tensor(np.stack([np.asarray(v) for v in vals])).float()
+                              if key == 'weak_targets' else torch.as_tensor(np.stack([np.asarray(v) for v in vals])))
+        elif key == 'seq_len':
+            batch[key] = [int(v) for v in vals]
+        else:
+            batch[key] = list(vals)
+    return batch
+
+
+class DeviceLoader:
+    """iterate device batches: the H2D copy of batch i+1 (pinned memory, copy stream) overlaps the
+    compute of batch i -- the eager counterpart of ``train.GraphedTrainStep.prefetch``."""
+
+    def __init__(self, batches, device):
+        self.batches, self.device = batches, torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _upload(self, batch):
+        out = {}
+        with torch.cuda.stream(self.stream):
+            for k, v in batch.items():
+                out[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            nxt = self._upload(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._upload(next(it))
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for v in cur.values():
+                if torch.is_tensor(v):
+                    v.record_stream(torch.cuda.current_stream(self.device))
+            yield cur

@@ -135,3 +135,26 @@ def test_reduce_and_mask_helpers_match_oracle():
     assert torch.equal(M.Max(axis=-1)(x, sl)[0], P.Max(axis=-1)(x, sl)[0])
     assert torch.equal(M.compute_mask(x, sl, 0, -1), P.compute_mask(x, sl, 0, -1))
     assert torch.equal(M.Pad('both')(x, 5), P.Pad('both')(x, 5))
+
+
+def test_collate_pads_sorts_and_keeps_lists():
+    """fetcher.py:36-51 + Collate(): sorted by seq_len descending, zero padded, lists kept."""
+    from pb_sed_b200.data import collate
+    rng = np.random.RandomState(0)
+    ex = []
+    for i, (S, T) in enumerate([(3000, 10), (5000, 16), (4000, 13)]):
+        ex.append({'example_id': f'e{i}', 'dataset': 'd', 'audio_data': rng.randn(1, S).astype(np.float32),
+                   'stft': rng.randn(1, T, 5, 2).astype(np.float32), 'seq_len': T,
+                   'weak_targets': np.eye(4, dtype=np.float32)[i], 'boundary_targets': rng.rand(4, T).astype(np.float32)})
+    b = collate(ex)
+    assert b['example_id'] == ['e1', 'e2', 'e0'] and b['seq_len'] == [16, 13, 10] and b['dataset'] == ['d'] * 3
+    assert b['stft'].shape == (3, 1, 16, 5, 2) and b['audio_data'].shape == (3, 1, 5000)
+    assert b['boundary_targets'].shape == (3, 4, 16) and b['weak_targets'].shape == (3, 4)
+    assert float(b['stft'][2, :, 10:].abs().max()) == 0. and float(b['audio_data'][2, :, 3000:].abs().max()) == 0.
+    assert np.array_equal(b['stft'][2, :, :10].numpy(), ex[0]['stft'])
+    assert np.array_equal(b['weak_targets'].numpy(), np.eye(4, dtype=np.float32)[[1, 2, 0]])
+    # audio-only examples: seq_len from the reference STFT geometry (provider.py:315-323), stft dropped
+    b2 = collate([{k: v for k, v in e.items() if k not in ('stft', 'seq_len', 'boundary_targets')} for e in ex])
+    from oracle import pt_port as P
+    assert b2['seq_len'] == [P.stft_frames(5000), P.stft_frames(4000), P.stft_frames(3000)] and 'stft' not in b2
+    assert 'stft' not in collate(ex, keep_stft=False)

@@ -523,3 +523,21 @@ def test_freeze_stops_gradients_of_the_first_layers():
             assert not p.requires_grad and p.grad is None, n
         else:
             assert p.grad is not None and maxdiff(p.grad, q.grad) < 1e-5 * max(1., float(q.grad.abs().max())), n
+
+
+def test_device_loader_double_buffers_pinned_batches():
+    from pb_sed_b200.data import collate, DeviceLoader
+    rng = np.random.RandomState(1)
+    batches = []
+    for j in range(4):
+        ex = [{'example_id': f'{j}_{i}', 'audio_data': rng.randn(1, 3000 + 100 * i).astype(np.float32),
+               'weak_targets': rng.rand(4).astype(np.float32)} for i in range(3)]
+        batches.append(collate(ex, stft_kwargs=TINY_STFT))
+    assert batches[0]['audio_data'].is_pinned()
+    seen = 0
+    for host, dev_b in zip(batches, DeviceLoader(batches, DEV)):
+        assert dev_b['audio_data'].is_cuda and dev_b['example_id'] == host['example_id']
+        assert torch.equal(dev_b['audio_data'].cpu(), host['audio_data'])
+        assert torch.equal(dev_b['weak_targets'].cpu(), host['weak_targets'])
+        seen += 1
+    assert seen == 4
