@@ -933,6 +933,10 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   const int units = p.B * p.F_out * cdiv(p.T, WG_TB);
   int rs = (2 * 148) / roles;                       // <= 2 CTAs per SM's worth, never a ragged extra wave
   if (rs >= 8 * 2 && units / rs < 4) rs = 148 / roles;
+  // 128-wide input slices need 147 KB of shared memory: ONE CTA per SM, so 2 x 148 CTAs would run as two
+  // back-to-back waves and pay TMEM allocation, pipeline fill and the atomic epilogue twice per SM
+  static const int wg_waves = getenv("PBSED_WG_WAVES") ? atoi(getenv("PBSED_WG_WAVES")) : 1;
+  if (p.Nc == 128 && wg_waves == 1 && 148 / roles >= 1) rs = 148 / roles;
   if (rs > units) rs = units;
   if (rs < 1) rs = 1;
   p.row_splits = rs;
