@@ -14,6 +14,16 @@ PARITY STATUS — read before trusting a number checked against this oracle:
   vectors under ``tests/golden/`` were produced by importing the *real*
   pb_sed classes from ``/root/reference`` (``tests/golden/make_golden.py``)
   on top of the module restatements in this package.
+* pb_sed-owned post-processing and inference drivers (``pb_sed/filters.py`` medfilt / stepfilt,
+  ``pb_sed/models/base/inference.py`` filtering / boundariesfilt / masking / the tagging, boundaries and
+  SED drivers, ``pb_sed/utils/segment.py`` merge_segments) is **pinned** the same way:
+  ``oracle/filters.py`` is checked against ``tests/golden/filters.npz`` (real functions,
+  ``tests/golden/make_golden_filters.py``) and the GPU drivers against
+  ``tests/golden/inference_tiny.npz`` (real drivers on the real FBCRNN class,
+  ``tests/golden/make_golden_inference.py``).
+* train-time augmentation (mel warping, time / frequency masks, noise, time-warped STFT grid) is a
+  restatement from the call-site kwargs only; where the upstream formula could not be recalled the
+  oracle DEFINES it (see ``pt_port.warp_mel`` / ``time_warp_grid``)  ->  **parity unpinned**.
 * third-party arithmetic (padertorch@b7ba24a / paderbox@809b272: STFT,
   mel filterbank, Normalization, CNN2d/CNN1d, GRU wrapper, reductions) is a
   restatement from the published algorithm; neither package is vendored in
