@@ -158,3 +158,41 @@ def test_collate_pads_sorts_and_keeps_lists():
     from oracle import pt_port as P
     assert b2['seq_len'] == [P.stft_frames(5000), P.stft_frames(4000), P.stft_frames(3000)] and 'stft' not in b2
     assert 'stft' not in collate(ex, keep_stft=False)
+
+
+def test_augmentation_samplers_follow_the_configured_distributions():
+    """the device-side draws (here on CPU tensors) of NormalizedLogMelExtractor.sample_augmentation:
+    LogTruncatedNormal(scale .08, truncation log 1.3), TruncatedExponential(scale .5, truncation 5),
+    uniform mask widths / onsets, uniform noise scale (training.py:195-216) -- checked against scipy."""
+    from scipy import stats
+    from pb_sed_b200.modules import NormalizedLogMelExtractor
+
+    class Seq:
+        dev = None
+    torch.manual_seed(0)
+    fe = NormalizedLogMelExtractor(
+        16000, 1024, 128, n_time_masks=2, max_masked_time_steps=70, max_masked_time_rate=.2,
+        n_frequency_masks=1, max_masked_frequency_bands=20, max_masked_frequency_rate=.2, max_noise_scale=.2,
+        frequency_warping_fn={'warp_factor_sampling_fn': {'scale': .08, 'truncation': np.log(1.3)},
+                              'boundary_frequency_ratio_sampling_fn': {'scale': .5, 'truncation': 5.},
+                              'highest_frequency': 8000.})
+    n = 20000
+    aug = fe.sample_augmentation(n, 8, Seq, 'cpu', False)          # T = 8 keeps the noise tensor small
+    la = np.log(aug['alpha'].numpy().astype(np.float64))
+    a = np.log(1.3) / .08
+    assert np.abs(la).max() <= np.log(1.3) + 1e-6
+    assert stats.kstest(la, stats.truncnorm(-a, a, scale=.08).cdf).pvalue > 1e-3
+    r = aug['ratio'].numpy().astype(np.float64)
+    assert r.min() >= 0 and r.max() <= 5.
+    assert stats.kstest(r, stats.truncexpon(b=5. / .5, scale=.5).cdf).pvalue > 1e-3
+    ns = aug['noise_scale'].numpy()
+    assert stats.kstest(ns, stats.uniform(0, .2).cdf).pvalue > 1e-3
+    # masks on a 500-frame clip: width ~ U{0..70}, onset ~ U{0..500-width}
+    lens = torch.full((n,), 500.)
+    m = NormalizedLogMelExtractor._masks(1, lens, 70, .2, 'cpu').numpy()[:, 0]
+    w, on = m[:, 1], m[:, 0]
+    assert w.min() == 0 and w.max() == 70 and abs(w.mean() - 35.) < 1. and (on + w <= 500).all() and on.min() >= 0
+    counts = np.bincount(w, minlength=71)
+    assert stats.chisquare(counts).pvalue > 1e-3
+    short = NormalizedLogMelExtractor._masks(1, torch.full((n,), 40.), 70, .2, 'cpu').numpy()[:, 0]
+    assert short[:, 1].max() == 8 and (short.sum(-1) <= 40).all()      # min(70, floor(.2 * 40)) = 8
