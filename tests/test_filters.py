@@ -107,3 +107,20 @@ def test_gpu_filters_full_size_rows_vs_oracle(built_lib):
     # idempotent under a second pass without a step filter
     again = GF.boundariesfilt(gotb, 0)
     assert torch.equal(again, gotb)
+
+
+@pytest.mark.gpu
+def test_gpu_medfilt_long_rows_use_the_bit_serial_kernel(built_lib):
+    """T > 512 (clips longer than ~10 s): the rank-selection fallback kernel, still bit-exact; negative
+    values and exact zeros exercise the analytic zero padding of both kernels."""
+    from pb_sed_b200 import filters as GF
+    rng = np.random.RandomState(2)
+    for T in (600, 512, 300):
+        x = rng.randn(3, 4, T).astype(np.float32)
+        x[0, 0, 10:40] = 0.
+        x[1, 2] = -np.abs(x[1, 2])
+        seq_len = np.array([T, T - 7, T // 3])
+        lens = np.array([3, 21, 101, 2 * (T // 2) + 1])
+        ref = OF.post_process(x, seq_len, medfilt_length=lens)
+        got = GF.post_process(torch.from_numpy(x).cuda(), seq_len, medfilt_length=lens)
+        assert np.array_equal(got.cpu().numpy(), ref), T
