@@ -182,7 +182,7 @@ struct __align__(16) SmemCtl {
 // FW_PROD producer / epilogue threads (4 or 8 warps), then one MMA warp and one weight-loader warp.
 // 8 warps feed the big tiles faster; 4 keep more CTAs co-resident for the narrow, latency-bound layers.
 template <int MT, int NBUF, int FW_PROD>
-__global__ void __launch_bounds__(FW_PROD + 64, NBUF == 2 ? 2 : (FW_PROD == 128 ? 4 : 1))
+__global__ void __launch_bounds__(FW_PROD + 64, FW_PROD == 128 ? 4 : (MT <= 2 ? 2 : 1))   // MT <= 2: two CTAs per SM must stay resident (<= 96 registers)
 tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const float* __restrict__ img, const float* __restrict__ bias,
@@ -320,19 +320,19 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     const int lw = warp & 3, chalf = warp >> 2;             // TMEM lane quarter, column half
     for (int mt = 0; mt < mt_count; ++mt) {
       const int row = lw * 32 + lane;
-      const int t = t0 + mt * TILE_M + row;
+      const int tbase = t0 + mt * TILE_M;
       if (ep_src) {
-        // stage the ReLU-mask source tile with row-contiguous loads (tile2 doubles as its buffer: the
-        // batch-norm-backward product overwrites each element in place)
-        const int tb0 = t0 + mt * TILE_M;
+        // the ReLU-mask source tile (= the layer input x, also needed for the batch-norm-backward product)
+        // is fetched with ASYNCHRONOUS 16-byte copies straight into shared memory while the accumulators
+        // are drained from TMEM below; rows behind the clip end are zero-filled (src-size 0)
         for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
           const int r = idx / nq, q = idx - r * nq;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (tb0 + r < len_b)
-            x = __ldg(reinterpret_cast<const float4*>(ep_src + (orow0 + tb0 + r) * p.out_stride + n0 + 4 * q));
-          *reinterpret_cast<float4*>(tile2 + r * LDT + 4 * q) = x;
+          const bool ok = tbase + r < len_b;
+          const float* src = ep_src + (orow0 + (ok ? tbase + r : t0)) * p.out_stride + n0 + 4 * q;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                       ::"r"(smem_u32(tile2 + r * LDT + 4 * q)), "l"(src), "r"(ok ? 16 : 0) : "memory");
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
       for (int cc = chalf * 16; cc < N; cc += FW_PROD / 8) {
         float v[16];
@@ -344,37 +344,47 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + j));
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           }
-          if (ep_src) {
-            const float4 x = *reinterpret_cast<const float4*>(tile2 + row * LDT + cc + j);
-            float4 s = x;
-            if (t >= len_b) s = make_float4(0.f, 0.f, 0.f, 0.f);
-            else if (ep_scale) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + cc + j));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + cc + j));
-              s.x = fmaf(s.x, sc.x, sh.x); s.y = fmaf(s.y, sc.y, sh.y);
-              s.z = fmaf(s.z, sc.z, sh.z); s.w = fmaf(s.w, sc.w, sh.w);
-            }
-            o.x = s.x > 0.f ? o.x : 0.f; o.y = s.y > 0.f ? o.y : 0.f;
-            o.z = s.z > 0.f ? o.z : 0.f; o.w = s.w > 0.f ? o.w : 0.f;
-            if (ep_sums) {
-              const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + ep_base + cc + j));
-              const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + ep_base + cc + j));
-              float4 o2;
-              o2.x = o.x * (x.x - mu.x) * rs.x; o2.y = o.y * (x.y - mu.y) * rs.y;
-              o2.z = o.z * (x.z - mu.z) * rs.z; o2.w = o.w * (x.w - mu.w) * rs.w;
-              *reinterpret_cast<float4*>(tile2 + row * LDT + cc + j) = o2;
-            }
-          }
           *reinterpret_cast<float4*>(tile + row * LDT + cc + j) = o;
         }
       }
+      if (ep_src) asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
-      const int tbase = t0 + mt * TILE_M;
-      for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
-        const int r = idx / nq, q = idx - r * nq;
-        if (tbase + r < p.T)
-          *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) =
-              *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
+      if (ep_src) {
+        // mask pass on the row-contiguous mapping: out = acc * [affine(x) > 0] * [t < len], stored straight
+        // to global; the masked value (and acc * xhat for the batch-norm-backward sums) go back to the tiles
+        for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
+          const int r = idx / nq, q = idx - r * nq;
+          float4 o = *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
+          const float4 x = *reinterpret_cast<const float4*>(tile2 + r * LDT + 4 * q);
+          float4 sv = x;
+          if (tbase + r >= len_b) sv = make_float4(0.f, 0.f, 0.f, 0.f);
+          else if (ep_scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + ep_base + 4 * q));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + ep_base + 4 * q));
+            sv.x = fmaf(sv.x, sc.x, sh.x); sv.y = fmaf(sv.y, sc.y, sh.y);
+            sv.z = fmaf(sv.z, sc.z, sh.z); sv.w = fmaf(sv.w, sc.w, sh.w);
+          }
+          o.x = sv.x > 0.f ? o.x : 0.f; o.y = sv.y > 0.f ? o.y : 0.f;
+          o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
+          if (tbase + r < p.T)
+            *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) = o;
+          if (ep_sums || out_stats) *reinterpret_cast<float4*>(tile + r * LDT + 4 * q) = o;
+          if (ep_sums) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + ep_base + 4 * q));
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + ep_base + 4 * q));
+            *reinterpret_cast<float4*>(tile2 + r * LDT + 4 * q) =
+                make_float4(o.x * (x.x - mu.x) * rs.x, o.y * (x.y - mu.y) * rs.y,
+                            o.z * (x.z - mu.z) * rs.z, o.w * (x.w - mu.w) * rs.w);
+          }
+        }
+        if (ep_sums || out_stats) asm volatile("bar.sync 1, %0;" ::"n"(FW_PROD) : "memory");
+      } else {
+        for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
+          const int r = idx / nq, q = idx - r * nq;
+          if (tbase + r < p.T)
+            *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) =
+                *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
+        }
       }
       if (out_stats || ep_sums) {
         // all 256 threads: (row group rg, column c); partial sums meet in shared-memory atomics and
