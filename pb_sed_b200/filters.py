@@ -8,7 +8,6 @@ their individual (per class / per hyper-parameter set) filter lengths.  Same fun
 argument meaning and result dtypes as the reference; tensors are CUDA tensors, ``axis`` must be the
 last (time) axis.
 """
-import ctypes
 
 import numpy as np
 import torch

@@ -14,7 +14,6 @@ Mirrors the slice of ``padertorch.train`` pb_sed drives
 * ``GraphedTrainStep`` captures forward+loss+backward+optimizer into one CUDA graph over static
   input buffers (shapes are static for fixed-length clips) and replays it per batch.
 """
-import ctypes
 
 import numpy as np
 import torch

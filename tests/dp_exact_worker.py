@@ -11,7 +11,6 @@ inside the forward/backward graph).  Prints ``DP_EXACT_OK`` on success.
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

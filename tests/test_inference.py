@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import ref_loader
-from util import GOLDEN, TINY_STFT
+from util import GOLDEN
 
 
 def test_segment_batch_and_merge_round_trip():
