@@ -356,23 +356,37 @@ class _CNN(nn.Module):
                 relu = i > 0
             fh = conv.flatten_height
             assert F_in == fh or fh == 1, (F_in, fh)
+            weight, taps = conv.weight, conv.taps
+            if fh > 1 and len(taps) > ops._lib.MAX_TAPS:
+                # a tall flatten ('b c f t -> b (c f) t' with f * k taps beyond the kernel's tap table, e.g. the
+                # un-pooled doctest net of weak_label/crnn.py:16-34: 80 bands x k = 3): materialise it once --
+                # (B,F,T,C) -> (B,1,T,F*C), channel index f*C + c, which is exactly the per-(f,c) norm index --
+                # and run the same contraction as a plain 1-D conv over F*C channels
+                k = len(taps) // fh
+                x = x.permute(0, 2, 1, 3).reshape(B, 1, T, fh * x.shape[3])
+                weight = weight.view(fh, k, weight.shape[1], weight.shape[2]).permute(1, 2, 0, 3) \
+                    .reshape(k, weight.shape[1], fh * weight.shape[2])
+                taps = [(0, dt) for (_, dt) in taps[:k]]
+                if stats is not None and stats.shape[0] < fh * conv.in_channels:
+                    stats = None
+                F_in, fh = 1, 1
             # does the consumer of this layer's output normalise with batch statistics?  then the conv
             # epilogue accumulates them (pooled layers: the statistics are of the pooled map -> own pass)
             if i + 1 < n:
                 want, want_pf = self.training and self._input_norm(i + 1) is not None, False
             else:
                 want, want_pf = self.training and next_stats is not None, next_stats == 'fc'
-            cfg = dict(F_in=F_in, F_out=1 if fh > 1 else F_in, taps=conv.taps, relu=relu,
+            cfg = dict(F_in=F_in, F_out=1 if fh > 1 else F_in, taps=taps, relu=relu,
                        per_f=fh > 1, pool=self._pool(self.pool_sizes[i]), norm=norm is not None,
                        eps=norm.eps if norm is not None else 0.,
                        momentum=norm.momentum if norm is not None else 0.,
                        training=self.training, want_stats=want, stats_per_f=want_pf)
             if norm is not None:
-                x, stats = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, norm.scale, norm.shift,
+                x, stats = ops.ConvLayerFn.apply(x, weight, conv.bias, norm.scale, norm.shift,
                                                  norm.running_mean, norm.running_power,
                                                  norm.num_tracked_values, seq, cfg, stats)
             else:
-                x, stats = ops.ConvLayerFn.apply(x, conv.weight, conv.bias, None, None, None, None, None,
+                x, stats = ops.ConvLayerFn.apply(x, weight, conv.bias, None, None, None, None, None,
                                                  seq, cfg, None)
             if stats.numel() == 0:
                 stats = None

@@ -247,7 +247,7 @@ def _grad_target(p):
     fresh zero buffer that is returned to autograd."""
     if p is None or not p.requires_grad:
         return None, None
-    if p.grad is not None:
+    if p.is_leaf and p.grad is not None:
         return p.grad, None
     g = torch.zeros_like(p)
     return g, g

@@ -541,3 +541,57 @@ def test_device_loader_double_buffers_pinned_batches():
         assert torch.equal(dev_b['weak_targets'].cpu(), host['weak_targets'])
         seen += 1
     assert seen == 4
+
+
+# ------------------------------------------------------------------ the reference's own (doctest) shape contracts
+def test_reference_doctest_contract_weak_label_crnn():
+    """pb_sed/models/weak_label/crnn.py:16-34: stft (4,1,15,257,2) -> scores (4,10,15), review runs.  The
+    un-pooled 80-band net flattens 32 x 80 features into the first CNN1d layer (tall-flatten path)."""
+    from pb_sed_b200.models import weak_label
+    cfg = {
+        'cnn': {'factory': 'CNN', 'cnn_2d': {'out_channels': [32, 32, 32], 'kernel_size': 3},
+                'cnn_1d': {'out_channels': [32, 32], 'kernel_size': 3}},
+        'rnn_fwd': {'factory': 'GRU', 'rnn': {'hidden_size': 64},
+                    'output_net': {'out_channels': [32, 10], 'kernel_size': 1}},
+        'feature_extractor': {'sample_rate': 16000, 'stft_size': 512, 'number_of_filters': 80},
+    }
+    torch.manual_seed(0)
+    crnn = weak_label.CRNN.from_config_dict(cfg).to(DEV).train()
+    np.random.seed(3)
+    inputs = {'stft': torch.tensor(np.random.randn(4, 1, 15, 257, 2), dtype=torch.float32, device=DEV),
+              'seq_len': [15, 14, 13, 12], 'weak_targets': torch.zeros((4, 10), device=DEV),
+              'boundary_targets': torch.zeros((4, 10, 15), device=DEV)}
+    outputs = crnn({**inputs})
+    assert outputs[0].shape == torch.Size([4, 10, 15]) and outputs[1].shape == torch.Size([4, 10, 15])
+    review = crnn.review(inputs, outputs)
+    assert torch.isfinite(review['loss']) and review['loss'].dim() == 0
+    review['loss'].backward()
+    g = [p.grad for p in crnn.parameters() if p.grad is not None]
+    assert len(g) > 10 and all(torch.isfinite(x).all() for x in g)
+    assert float(crnn.cnn.cnn_1d.convs[0].weight.grad.abs().max()) > 0        # gradient reaches the flatten conv
+    crnn.eval()
+    with torch.no_grad():
+        assert crnn.tagging({**inputs})[0].shape == (4, 10, 1)
+
+
+def test_reference_doctest_contract_strong_label_crnn():
+    """pb_sed/models/strong_label/crnn.py:21-45: stft (4,1,5,257,2) -> scores (4,10,5), review runs."""
+    from pb_sed_b200.models import strong_label
+    cfg = {
+        'cnn': {'factory': 'CNN', 'cnn_2d': {'out_channels': [32, 32, 32], 'kernel_size': 3},
+                'cnn_1d': {'out_channels': [32, 32], 'kernel_size': 3}},
+        'rnn': {'factory': 'GRU', 'rnn': {'bidirectional': True, 'hidden_size': 64, 'num_layers': 2},
+                'output_net': {'out_channels': [32, 10], 'kernel_size': 1}},
+        'feature_extractor': {'sample_rate': 16000, 'stft_size': 512, 'number_of_filters': 80},
+    }
+    torch.manual_seed(0)
+    crnn = strong_label.CRNN.from_config_dict(cfg).to(DEV).train()
+    assert crnn.rnn.output_net.in_channels == 128
+    inputs = {'stft': torch.randn((4, 1, 5, 257, 2), device=DEV), 'seq_len': [5, 4, 3, 2],
+              'weak_targets': torch.zeros((4, 10), device=DEV), 'strong_targets': torch.zeros((4, 10, 5), device=DEV),
+              'tag_condition': torch.zeros((4, 10), device=DEV)}
+    outputs = crnn(dict(inputs))
+    assert outputs[0].shape == torch.Size([4, 10, 5])
+    review = crnn.review(inputs, outputs)
+    assert torch.isfinite(review['loss'])
+    review['loss'].backward()
