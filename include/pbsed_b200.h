@@ -34,6 +34,9 @@ extern "C" {
 int pbsed_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long pbsed_launch_count(void);
+/* name of the main kernel the most recent entry point dispatched (static string; bench.py's per-kernel
+ * roofline pass groups its per-call device timings by it) */
+const char* pbsed_last_kernel(void);
 
 /* ---------------------------------------------------------------------------
  * K1  STFT -> |.|^2 -> mel -> log      (replaces paderbox stft as configured at

@@ -278,6 +278,7 @@ class Normalization(nn.Module):
         self.momentum = momentum
         self.interpolation_factor = interpolation_factor
         self.track_running_stats = track_running_stats
+        self.frozen_stats = False      # [R] Normalization.freeze(freeze_stats=True): running statistics in train mode
         self.shift_on = shift
         self.scale_on = scale
         reduced = [1 if i in self.statistics_axis else s for i, s in enumerate(shape)]
@@ -310,7 +311,7 @@ class Normalization(nn.Module):
 
     def forward(self, x, sequence_lengths=None):
         mask = compute_mask(x, sequence_lengths, self.batch_axis, self.sequence_axis)
-        if self.training or not self.track_running_stats:
+        if (self.training and not self.frozen_stats) or not self.track_running_stats:
             _, n, mean, var = self._stats(x, sequence_lengths)
             y = x
             if self.shift_on:
@@ -378,7 +379,7 @@ class NormalizedLogMelExtractor(nn.Module):
         self.augment = augment  # oracle: deterministic path only
         fb = get_fbanks(sample_rate, stft_size, number_of_filters,
                         lowest_frequency, highest_frequency)
-        self.register_buffer('fbanks', torch.from_numpy(fb.T.copy()).float())  # (F, n_mels)
+        self.register_buffer('fbanks', torch.from_numpy(fb.T.copy()).float(), persistent=False)  # (F, n_mels)
         self.norm = Normalization(
             'bcft', (None, num_channels, number_of_filters, None), statistics_axis='bt',
             independent_axis=None, eps=norm_eps, momentum=None, interpolation_factor=1.)
@@ -445,6 +446,17 @@ class Pad(nn.Module):
         return F.pad(x, p)
 
 
+class _ConvBlock(nn.Module):
+    """[R] padertorch Conv1d / Conv2d module: ``conv`` (torch conv) + ``norm`` -> state-dict keys
+    ``convs.<i>.conv.{weight,bias}``, ``convs.<i>.norm.*`` ([CS] weak_label_crnn/training.py:331-340 reads the
+    layer index from the second dotted component)."""
+
+    def __init__(self, conv, norm):
+        super().__init__()
+        self.conv = conv
+        self.norm = norm
+
+
 class _CNN(nn.Module):
     """Shared stack logic of CNN1d / CNN2d.
 
@@ -475,13 +487,14 @@ class _CNN(nn.Module):
         norm_kwargs = dict(norm_kwargs or {})
         Conv = nn.Conv2d if self.ndim == 2 else nn.Conv1d
         self.convs = nn.ModuleList()
-        self.norms = nn.ModuleList()
+        norms = []
+        convs = []
         c = in_channels
         for i, co in enumerate(self.out_channels):
             conv = Conv(c, co, self.kernel_sizes[i])
             nn.init.xavier_uniform_(conv.weight)
             nn.init.zeros_(conv.bias)
-            self.convs.append(conv)
+            convs.append(conv)
             if pre_activation:
                 has_norm = not (i == 0 and input_layer)
                 nc = c
@@ -491,12 +504,18 @@ class _CNN(nn.Module):
             if norm == 'batch' and has_norm:
                 fmt = 'bcft' if self.ndim == 2 else 'bct'
                 shape = (None, nc, None, None) if self.ndim == 2 else (None, nc, None)
-                self.norms.append(Normalization(
+                norms.append(Normalization(
                     fmt, shape, statistics_axis='bft' if self.ndim == 2 else 'bt',
                     independent_axis='c', momentum=0.95, **norm_kwargs))
             else:
-                self.norms.append(None)
+                norms.append(None)
             c = co
+        for conv, norm in zip(convs, norms):
+            self.convs.append(_ConvBlock(conv, norm))
+
+    @property
+    def norms(self):
+        return [blk.norm for blk in self.convs]
 
     def _pad(self, x, k):
         if self.ndim == 2:
@@ -524,9 +543,9 @@ class _CNN(nn.Module):
                     x = torch.relu(self.norms[i](x, seq_len))
                 elif not (i == 0 and self.input_layer):
                     x = torch.relu(x)
-                x = self.convs[i](self._pad(x, self.kernel_sizes[i]))
+                x = self.convs[i].conv(self._pad(x, self.kernel_sizes[i]))
             else:
-                x = self.convs[i](self._pad(x, self.kernel_sizes[i]))
+                x = self.convs[i].conv(self._pad(x, self.kernel_sizes[i]))
                 if not (i == n - 1 and self.output_layer):
                     if self.norms[i] is not None:
                         x = self.norms[i](x, seq_len)
@@ -535,14 +554,16 @@ class _CNN(nn.Module):
         return x, seq_len
 
     def freeze(self, num_layers=None, freeze_norm_stats=True):
-        """[CS] experiments/weak_label_crnn/training.py:343-350."""
+        """[CS] experiments/weak_label_crnn/training.py:343-350.  [R] frozen norms with ``freeze_norm_stats``
+        use their running statistics in train mode and stop updating them."""
         n = len(self.convs) if num_layers is None else num_layers
         for i in range(n):
-            for p in self.convs[i].parameters():
+            for p in self.convs[i].conv.parameters():
                 p.requires_grad = False
             if self.norms[i] is not None:
                 for p in self.norms[i].parameters():
                     p.requires_grad = False
+                self.norms[i].frozen_stats = bool(freeze_norm_stats)
 
 
 class CNN2d(_CNN):

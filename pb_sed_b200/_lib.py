@@ -73,6 +73,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.restype = ret
         fn.argtypes = argtypes
+    lib.pbsed_last_kernel.restype = ctypes.c_char_p      # the one non-integer entry point
+    lib.pbsed_last_kernel.argtypes = []
     _lib = lib
     return lib
 
@@ -95,7 +97,7 @@ def call(name, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        profile_sink.append((name, e0, e1, args))
+        profile_sink.append((name, e0, e1, args, load().pbsed_last_kernel().decode()))
     else:
         rc = fn(*args)
     if rc != 0:

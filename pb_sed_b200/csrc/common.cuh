@@ -9,6 +9,8 @@
 #endif
 
 extern long long g_pbsed_launches;   // defined in api.cu
+extern const char* g_pbsed_last_kernel;   // name of the main kernel the last entry point dispatched (bench.py)
+static inline void pbsed_note_kernel(const char* name) { g_pbsed_last_kernel = name; }
 
 static inline int pbsed_after_launch() {
   ++g_pbsed_launches;

@@ -134,6 +134,7 @@ int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const f
   Cin1Params p;
   cin1_fill(d, p);
   dim3 grid(cdiv(p.T, 256), p.F_out, p.B);
+  pbsed_note_kernel("conv_cin1_fwd_kernel");
   if (p.Cout == 16) conv_cin1_fwd_kernel<16><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, W, bias, out);
   else              conv_cin1_fwd_kernel<32><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, W, bias, out);
   *handled = 1;
@@ -161,6 +162,7 @@ int conv_cin1_wgrad_dispatch(const pbsed_tapgemm_desc* d, const float* in, const
   if (gpc < 1) gpc = 1;
   dim3 grid(cdiv(total, gpc));
   cudaError_t e;
+  pbsed_note_kernel("conv_cin1_wgrad_kernel");
   if (p.Cout == 16) {
     e = cudaFuncSetAttribute(conv_cin1_wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -203,6 +203,7 @@ static int launch_fwd(const TapParams& p, const float* in, const float* scale, c
   const int n_tiles = cdiv(p.Cout, BN);
   dim3 grid(cdiv(p.T, BM) * n_tiles, p.F_out, p.B);
   if (grid.y > 65535 || grid.z > 65535) return PBSED_EINVAL;
+  pbsed_note_kernel("tapgemm_ffma_kernel");
   tapgemm_ffma_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(
       p, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, n_tiles);
   return pbsed_after_launch();
@@ -392,6 +393,7 @@ static int launch_wgrad(const TapParams& p, const float* in, const float* scale,
   if (gpc > 64) gpc = 64;
   dim3 grid(cdiv(total_groups, gpc), p.ntaps, n_tiles * c_tiles);
   if (grid.z > 65535) return PBSED_EINVAL;
+  pbsed_note_kernel("tapgemm_wgrad_kernel");
   tapgemm_wgrad_kernel<BN, BC, TN, TC, BKR><<<grid, (BN / TN) * (BC / TC), 0, st>>>(
       p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, gpc, c_tiles);
   return pbsed_after_launch();

@@ -899,6 +899,8 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   tapgemm_tc_kernel<MTV, NBV, PRV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
                                                   ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
                                                   d->no_input_mask ? nullptr : seq_len, t_super, (int)pad, stat_n);
+  pbsed_note_kernel(nbuf == 2 ? "tapgemm_tc_kernel<2,2,256>" : mt == 4 ? "tapgemm_tc_kernel<4,4,256>" : mt == 2 ? "tapgemm_tc_kernel<2,4,256>"
+                    : p.N <= 32 ? "tapgemm_tc_kernel<1,4,128>" : "tapgemm_tc_kernel<1,4,256>");
   if (nbuf == 2) { PBSED_TC_LAUNCH(2, 2, 256) } else if (mt == 4) { PBSED_TC_LAUNCH(4, 4, 256) } else if (mt == 2) { PBSED_TC_LAUNCH(2, 4, 256) }
   else if (p.N <= 32) { PBSED_TC_LAUNCH(1, 4, 128) } else { PBSED_TC_LAUNCH(1, 4, 256) }
 #undef PBSED_TC_LAUNCH
@@ -955,6 +957,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(rs, p.ngroups, p.m_slices * p.c_slices);
+  pbsed_note_kernel("wgrad_tc_kernel");
   wgrad_tc_kernel<<<grid, WG_PROD + 32, smem, st>>>(p, in, scale, shift, seq_len, dout, dW, dbias);
   *handled = 1;
   return pbsed_after_launch();

@@ -182,6 +182,7 @@ int launch_wm(const WmParams& p, const float* in, const float* scale, const floa
   const int units = p.B * p.F * cdiv(p.T, TT);
   int grid = 148 * 2;
   if (grid > units) grid = units;
+  pbsed_note_kernel("wgrad_mma_kernel");
   wgrad_mma_kernel<COUT, CIN><<<grid, 256, smem, st>>>(p, in, scale, shift, seq_len, dout, dW, dbias);
   return pbsed_after_launch();
 }

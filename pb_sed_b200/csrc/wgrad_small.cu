@@ -143,6 +143,7 @@ static int launch_ws(const WsParams& p, const float* in, const float* scale, con
   const int units = p.B * p.F * cdiv(p.T, 64);
   int grid = 148 * 4;
   if (grid > units) grid = units;
+  pbsed_note_kernel("wgrad_small_kernel");
   wgrad_small_kernel<COUT, CIN, NPT, CPT><<<grid, 256, 0, st>>>(p, in, scale, shift, seq_len, dout, dW, dbias);
   return pbsed_after_launch();
 }

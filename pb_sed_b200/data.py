@@ -110,3 +110,46 @@ class DeviceLoader:
                 if torch.is_tensor(v):
                     v.record_stream(torch.cuda.current_stream(self.device))
             yield cur
+
+
+class SyntheticClipStream:
+    """endless on-device stream of synthetic 10 s clips for the AudioSet-scale configuration (BASELINE.json
+    configs[4]: 2 M clips, K = 527, weak labels only; reference data path AudioSetProvider,
+    pb_sed/experiments/weak_label_crnn/training.py:113-128).  Every ``fill_`` draws a NEW batch from
+    torch's counter-based (Philox) CUDA generator -- nothing is stored, nothing crosses PCIe -- and is
+    CUDA-graph capturable (the generator's offset advances per replay), so ``GraphedTrainStep(input_fn=
+    stream.fill_)`` trains on a fresh batch every step.  Clips: 3-tap low-passed Gaussian noise plus one gated
+    sinusoid 'event', peak-normalised (audio reader ``normalization_type='max'``, provider.py:309-310);
+    labels: Bernoulli(labels_per_clip / K) with at least one active class."""
+
+    def __init__(self, batch, num_events, device, num_samples=160000, sample_rate=16000, labels_per_clip=2.7):
+        self.B, self.K, self.S = batch, num_events, num_samples
+        self.device = torch.device(device)
+        self.p = labels_per_clip / num_events
+        self.t = torch.arange(num_samples, device=self.device, dtype=torch.float32) / sample_rate
+        self.clips = 0
+
+    def example(self):
+        b = {'audio_data': torch.empty((self.B, 1, self.S), device=self.device),
+             'weak_targets': torch.empty((self.B, self.K), device=self.device),
+             'seq_len': [stft_num_frames(self.S, 320, 960)] * self.B}
+        self.fill_(b)
+        return b
+
+    def fill_(self, static):
+        B, S, dev = self.B, self.S, self.device
+        x = torch.randn((B, S + 2), device=dev)
+        y = x[:, 2:] + 1.6 * x[:, 1:-1] + .8 * x[:, :-2]
+        u = torch.rand((B, 4), device=dev)
+        f0 = 200. + 5800. * u[:, 0:1]
+        on = u[:, 1:2] * 8.
+        off = on + .1 + u[:, 2:3] * 5.
+        gate = ((self.t[None] >= on) & (self.t[None] < off)).float()
+        y = y + (1. + 4. * u[:, 3:4]) * gate * torch.sin(2. * np.pi * f0 * self.t[None])
+        y = y / y.abs().amax(-1, keepdim=True)
+        static['audio_data'].copy_(y[:, None])
+        weak = (torch.rand((B, self.K), device=dev) < self.p).float()
+        first = torch.randint(0, self.K, (B, 1), device=dev)
+        weak.scatter_(1, first, 1.)
+        static['weak_targets'].copy_(weak)
+        self.clips += B

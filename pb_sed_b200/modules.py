@@ -167,6 +167,7 @@ class Normalization(nn.Module):
         self.num_channels, self.ndim = num_channels, ndim
         self.eps, self.momentum = eps, momentum
         self.flatten = flatten
+        self.frozen_stats = False      # freeze(freeze_norm_stats=True): running statistics even in train mode
         if affine:
             self.scale = nn.Parameter(torch.ones(num_channels))
             self.shift = nn.Parameter(torch.zeros(num_channels))
@@ -269,6 +270,18 @@ class _Conv(nn.Module):
                 p.copy_((self._from_ref(v) if name == 'weight' else v).to(p.device, p.dtype))
 
 
+class _ConvBlock(nn.Module):
+    """one layer of a padertorch CNN: ``conv`` (weight, bias) and its ``norm`` (or None), so that the
+    state-dict keys read ``convs.<i>.conv.{weight,bias}`` / ``convs.<i>.norm.{scale,shift,running_*}`` like
+    padertorch's Conv modules -- the reference's init-checkpoint code takes the output layer's index from
+    ``sorted(keys)[-1].split('.')[1]`` (weak_label_crnn/training.py:331-340)."""
+
+    def __init__(self, conv, norm):
+        super().__init__()
+        self.conv = conv
+        self.norm = norm
+
+
 class _CNN(nn.Module):
     """CNN1d / CNN2d of padertorch.contrib.je.modules.conv (kwargs: training.py:218-242,250-259).
 
@@ -305,22 +318,28 @@ class _CNN(nn.Module):
         eps = nk.get('eps', 1e-3)
         momentum = nk.get('momentum', 0.95)
         self.convs = nn.ModuleList()
-        self.norms = nn.ModuleList()
         c = in_channels
         for i, co in enumerate(self.out_channels):
             fh = flatten_height if i == 0 else 1
-            self.convs.append(_Conv(self.ndim, c, co, ks[i], flatten_height=fh))
             if pre_activation:
                 has = not (i == 0 and input_layer)
                 nc, fl = c * fh, ((c, fh) if fh > 1 else None)
             else:
                 has = not (i == n - 1 and output_layer)
                 nc, fl = co, None
-            self.norms.append(Normalization(nc, self.ndim, eps=eps, momentum=momentum, flatten=fl)
-                              if (norm == 'batch' and has) else None)
             if norm not in ('batch', None):
                 raise NotImplementedError(norm)
+            self.convs.append(_ConvBlock(
+                _Conv(self.ndim, c, co, ks[i], flatten_height=fh),
+                Normalization(nc, self.ndim, eps=eps, momentum=momentum, flatten=fl)
+                if (norm == 'batch' and has) else None))
             c = co
+
+    @property
+    def norms(self):
+        """per layer: the Normalization stored with conv i (pre-activation: applied to its input;
+        post-activation: to its output), or None."""
+        return [blk.norm for blk in self.convs]
 
     def _pool(self, p):
         if p in (1, None, (1, 1)):
@@ -346,7 +365,8 @@ class _CNN(nn.Module):
         per (f, c)) for a following stack's first norm; then the result is (y, stats)."""
         n = len(self.convs)
         stats = stats_in
-        for i, conv in enumerate(self.convs):
+        for i, blk in enumerate(self.convs):
+            conv = blk.conv
             B, F_in, T, _ = x.shape
             if self.pre_activation:
                 norm = self.norms[i]
@@ -373,14 +393,20 @@ class _CNN(nn.Module):
             # does the consumer of this layer's output normalise with batch statistics?  then the conv
             # epilogue accumulates them (pooled layers: the statistics are of the pooled map -> own pass)
             if i + 1 < n:
-                want, want_pf = self.training and self._input_norm(i + 1) is not None, False
+                nxt = self._input_norm(i + 1)
+                want, want_pf = self.training and nxt is not None and not nxt.frozen_stats, False
             else:
                 want, want_pf = self.training and next_stats is not None, next_stats == 'fc'
+            # a frozen layer (freeze(..., freeze_norm_stats=True)) normalises with its running statistics even in
+            # train mode and does not update them (padertorch Normalization.freeze)
+            live = self.training and not (norm is not None and norm.frozen_stats)
+            if stats is not None and not live:
+                stats = None
             cfg = dict(F_in=F_in, F_out=1 if fh > 1 else F_in, taps=taps, relu=relu,
                        per_f=fh > 1, pool=self._pool(self.pool_sizes[i]), norm=norm is not None,
                        eps=norm.eps if norm is not None else 0.,
                        momentum=norm.momentum if norm is not None else 0.,
-                       training=self.training, want_stats=want, stats_per_f=want_pf)
+                       training=live, want_stats=want, stats_per_f=want_pf)
             if norm is not None:
                 x, stats = ops.ConvLayerFn.apply(x, weight, conv.bias, norm.scale, norm.shift,
                                                  norm.running_mean, norm.running_power,
@@ -401,14 +427,18 @@ class _CNN(nn.Module):
         return (from_native(y) if self.ndim == 2 else from_native(y.squeeze(1))), seq_len
 
     def freeze(self, num_layers=None, freeze_norm_stats=True):
-        """training.py:343-350."""
+        """training.py:343-350: stop the gradients of the first ``num_layers`` layers; with
+        ``freeze_norm_stats`` (the reference experiments' default) their norms also stop tracking: they use
+        the running statistics in train mode and leave them untouched."""
         n = len(self.convs) if num_layers is None else num_layers
         for i in range(n):
-            for p in self.convs[i].parameters():
+            for p in self.convs[i].conv.parameters():
                 p.requires_grad = False
-            if self.norms[i] is not None:
-                for p in self.norms[i].parameters():
+            norm = self.convs[i].norm
+            if norm is not None:
+                for p in norm.parameters():
                     p.requires_grad = False
+                norm.frozen_stats = bool(freeze_norm_stats)
 
 
 class CNN2d(_CNN):
@@ -450,7 +480,8 @@ class CNN(nn.Module):
             x = ops.ConcatCondFn.apply(x, cond)
         # the first cnn_1d norm is indexed per (f, c) of the cnn_2d output: its statistics come out of
         # the last cnn_2d conv's epilogue
-        want = 'fc' if (self.training and self.cnn_1d._input_norm(0) is not None) else None
+        n0 = self.cnn_1d._input_norm(0)
+        want = 'fc' if (self.training and n0 is not None and not n0.frozen_stats) else None
         if want:
             x, stats = self.cnn_2d.forward_native(x, seq, next_stats=want)
         else:
@@ -615,7 +646,7 @@ class NormalizedLogMelExtractor(nn.Module):
         self.lowest_frequency = lowest_frequency
         self.highest_frequency = sample_rate / 2 if highest_frequency is None else highest_frequency
         fb = mel_filterbank(sample_rate, stft_size, number_of_filters, lowest_frequency, highest_frequency)
-        self.register_buffer('fbanks', torch.from_numpy(fb.T.copy()).float())          # (F, n_mels)
+        self.register_buffer('fbanks', torch.from_numpy(fb.T.copy()).float(), persistent=False)   # (F, n_mels); not a checkpoint key
         lo, hi, w, stride = sparse_filterbank(fb.astype(np.float32))
         self.register_buffer('_fb_lo', torch.from_numpy(lo), persistent=False)
         self.register_buffer('_fb_hi', torch.from_numpy(hi), persistent=False)

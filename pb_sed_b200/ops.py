@@ -48,13 +48,17 @@ def enable_wgrad_stream(flag=True):
 class _WgradStream:
     """context: fork the side stream off the current one and keep the tensors it reads alive."""
 
-    def __init__(self, *tensors):
+    def __init__(self, *tensors, direct=True):
+        """direct: every gradient of this block is accumulated straight into an existing leaf ``.grad``
+        (the flat arena, joined by ``train.Adam``).  A gradient buffer that is RETURNED to autograd is
+        consumed on the current stream, so such blocks stay on the current stream."""
         self.tensors = [t for t in tensors if t is not None]
         self.ctx = None
+        self.direct = direct
 
     def __enter__(self):
         global _wgrad_stream
-        if not _wgrad_stream_enabled:
+        if not _wgrad_stream_enabled or not self.direct:
             return self
         if _wgrad_stream is None:
             _wgrad_stream = torch.cuda.Stream()
@@ -349,7 +353,7 @@ class ConvLayerFn(torch.autograd.Function):
         dW, dW_ret = _grad_target(w_p)
         db, db_ret = _grad_target(b_p)
         if dW is not None:
-            with _WgradStream(x, dz, scale, shift):
+            with _WgradStream(x, dz, scale, shift, direct=dW_ret is None and db_ret is None):
                 tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq if cfg['norm'] else None, mask_out=False)
         dx = dg_ret = dbe_ret = None
         # the data-gradient pass is also what yields this layer's OWN norm gradients (dgamma, dbeta): it must
@@ -486,7 +490,7 @@ class GruMultiFn(torch.autograd.Function):
             dbih, r2 = _grad_target(p_bih)
             dbhh, r3 = _grad_target(p_bhh)
             dx = None
-            with _WgradStream(x, h, dgis[g], dghs[g]):
+            with _WgradStream(x, h, dgis[g], dghs[g], direct=all(r is None for r in (r0, r1, r2, r3))):
                 for d in range(nd):
                     if dwih is not None:
                         tapgemm_wgrad(x, dgis[g][d], make_desc(B, 1, 1, T, In, H3, [(0, 0)]), dwih[d],

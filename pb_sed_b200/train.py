@@ -148,8 +148,10 @@ class GraphedTrainStep:
     """whole train step as ONE CUDA graph.  ``example`` is a batch dict of CUDA tensors whose shapes
     stay fixed; ``__call__(batch)`` copies the new batch into the static buffers and replays."""
 
-    def __init__(self, model, optimizer, example, warmup=2):
-        self.model, self.optimizer = model, optimizer
+    def __init__(self, model, optimizer, example, warmup=2, input_fn=None):
+        """input_fn(static): optional, captured at the head of the graph -- refills the static input buffers
+        in place on the device (``data.SyntheticClipStream.fill_``), so every replay trains on a new batch."""
+        self.model, self.optimizer, self.input_fn = model, optimizer, input_fn
         model.train()
         saved = getattr(model, 'emit_buffers', None)
         if saved is not None:
@@ -176,8 +178,11 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph_update):
                 self.grad_norm = self.optimizer.update(join=False)     # joined at the end of the first graph
         self.optimizer.arena.rebind_grads()
+        self._static_out = (self.loss, self.grad_norm)      # the graph's own result buffers
 
     def _fwd_bwd(self):
+        if self.input_fn is not None:
+            self.input_fn(self.static)
         outputs = self.model(dict(self.static))
         loss = self.model.review(self.static, outputs)['loss']
         loss.backward()
@@ -200,7 +205,15 @@ class GraphedTrainStep:
                 g.reset()
                 setattr(self, name, None)
 
+    def _same_lengths(self, batch):
+        """sequence lengths (a host list) are baked into the captured graph: masks, batch-norm counts, loss
+        denominators and the augmentation limits all derive from them at capture time."""
+        a, b = batch.get('seq_len'), self.static.get('seq_len')
+        return a is None or b is None or [int(v) for v in a] == [int(v) for v in b]
+
     def load(self, batch):
+        assert self._same_lengths(batch), \
+            'GraphedTrainStep: seq_len differs from the captured batch (use __call__, which falls back to an eager step)'
         for k, v in batch.items():
             if torch.is_tensor(v):
                 self.static[k].copy_(v, non_blocking=True)
@@ -224,7 +237,7 @@ class GraphedTrainStep:
                 if torch.is_tensor(v):
                     self._stage[i][k].copy_(v, non_blocking=True)
             self._stage_ready[i].record()
-        self._pending = i
+        self._pending, self._pending_seq_len = i, host_batch.get('seq_len')
         self._stage_idx = i ^ 1
 
     def step_prefetched(self):
@@ -232,16 +245,35 @@ class GraphedTrainStep:
         i = self._pending
         cur = torch.cuda.current_stream()
         cur.wait_event(self._stage_ready[i])
+        if not self._same_lengths({'seq_len': self._pending_seq_len}):
+            batch = dict({k: v.clone() for k, v in self._stage[i].items()}, seq_len=self._pending_seq_len)
+            self._stage_free[i].record(cur)
+            return self(batch)                                  # other clip lengths: eager step (see __call__)
         for k, v in self._stage[i].items():
             self.static[k].copy_(v, non_blocking=True)          # device-to-device, microseconds
         self._stage_free[i].record(cur)
         return self()
 
     def __call__(self, batch=None):
+        """replay the captured step on ``batch`` (None: whatever the static buffers hold).  A batch whose
+        ``seq_len`` differs from the captured one (ragged batches of ``data.collate``) cannot reuse the graph:
+        it runs as an eager ``train_step`` -- same arithmetic, same optimizer state, un-graphed speed."""
+        if batch is not None and not self._same_lengths(batch):
+            if not getattr(self, '_warned', False):
+                import warnings
+                warnings.warn('GraphedTrainStep: batch with different seq_len -> eager step (bucket clips by '
+                              'length, or capture one graph per length pattern, to stay on the graph path)')
+                self._warned = True
+            merged = {k: v for k, v in self.static.items() if not torch.is_tensor(v)}
+            merged.update(batch)
+            self.loss, self.grad_norm = train_step(self.model, self.optimizer, merged)
+            self.optimizer.arena.rebind_grads()
+            return self.loss, self.grad_norm
         if batch is not None:
             self.load(batch)
         self.graph.replay()
         if self.split:
             self.optimizer.allreduce_grads()
             self.graph_update.replay()
+        self.loss, self.grad_norm = self._static_out
         return self.loss, self.grad_norm

@@ -18,6 +18,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(built_lib, name), name
     assert built_lib.pbsed_abi_version() == 5
     assert built_lib.pbsed_launch_count() >= 0
+    assert isinstance(built_lib.pbsed_last_kernel(), bytes)      # const char* entry point (not an int prototype)
 
 
 def test_bad_arguments_return_einval_without_touching_the_gpu(built_lib):
@@ -66,6 +67,42 @@ def test_state_dict_interchanges_with_reference_layout():
         fresh = OM.build_fbcrnn(seed=9) if ora2 == 'FBCRNN' else OM.build_bicrnn(seed=9)
         fresh.load_state_dict(sd, strict=True)          # and back into torch modules
     assert sum(p.numel() for p in weak_label.CRNN.from_config_dict(config.fbcrnn_config()).parameters()) == 3493188
+
+
+def test_state_dict_keys_follow_padertorch_and_the_init_checkpoint_recipe():
+    """checkpoint keys nest as ``convs.<i>.conv.{weight,bias}`` / ``convs.<i>.norm.*`` (padertorch Conv modules);
+    the reference's init-checkpoint code (weak_label_crnn/training.py:327-342) pops the output layer by the
+    second dotted component of the LAST sorted key -- run that recipe verbatim on our state dict."""
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label
+    src = weak_label.CRNN.from_config_dict(config.tiny_fbcrnn_config(num_events=10))
+    dst = weak_label.CRNN.from_config_dict(config.tiny_fbcrnn_config(num_events=7))   # other label set
+    sd = src.state_dict()
+    keys = set(sd)
+    assert 'cnn.cnn_2d.convs.0.conv.weight' in keys and 'cnn.cnn_2d.convs.1.norm.running_mean' in keys
+    assert 'cnn.cnn_2d.convs.0.norm.scale' not in keys               # bare input layer
+    assert 'rnn_fwd.output_net.convs.0.norm.scale' in keys and 'rnn_fwd.output_net.convs.1.conv.bias' in keys
+    assert not any('fbanks' in k or k.split('.')[-2] == 'norms' for k in keys)
+    assert 'rnn_fwd.rnn.weight_hh_l1' in keys and 'feature_extractor.norm.running_power' in keys
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    dst.cnn.load_state_dict(sub('cnn.'))
+    dst.rnn_fwd.rnn.load_state_dict(sub('rnn_fwd.rnn.'))
+    out_fwd, out_bwd = sub('rnn_fwd.output_net.'), sub('rnn_bwd.output_net.')
+    param_keys = sorted(out_fwd.keys())
+    layer_idx = [key.split('.')[1] for key in param_keys]
+    last_layer_idx = layer_idx[-1]
+    assert last_layer_idx == '1'                                     # the output layer, not a norm of layer 0
+    for key, idx in zip(param_keys, layer_idx):
+        if idx == last_layer_idx:
+            out_fwd.pop(key)
+            out_bwd.pop(key)
+    dst.rnn_fwd.output_net.load_state_dict(out_fwd, strict=False)
+    dst.rnn_bwd.output_net.load_state_dict(out_bwd, strict=False)
+    assert torch.equal(dst.rnn_fwd.output_net.convs[0].conv.weight, src.rnn_fwd.output_net.convs[0].conv.weight)
+    assert dst.rnn_fwd.output_net.convs[1].conv.weight.shape[1] == 7
+    assert torch.equal(dst.cnn.cnn_2d.convs[2].norm.running_power, src.cnn.cnn_2d.convs[2].norm.running_power)
 
 
 def test_native_conv_weight_layout_is_the_tap_contraction():

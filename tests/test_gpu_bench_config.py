@@ -1,0 +1,244 @@
+"""GPU (-m gpu): parity at the configurations bench.py actually times (BASELINE.json configs[1] and
+configs[3]).  Tile / cluster shapes are chosen from the batch size inside the library, so the small-batch
+tests of test_gpu_parity.py / test_gpu_tc.py run different kernel instantiations than a B = 32 step; the
+tests here feed the benchmark's own shapes (B = 32 full-size FBCRNN, ragged and equal-length; every conv
+layer's forward / data-gradient / weight-gradient launch at B = 32; the H = 256 GRU at B = 32 and 33 with
+its ragged tail cluster; the tag-conditioned BiCRNN at B = 64) and compare against the CPU oracle or
+the exact-fp32 FFMA kernels.  Tolerances are written next to each comparison."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM, pt_port as P
+from util import ref_layout_grads, maxdiff, reldiff
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+TAPS_3x3 = [(i - 1, j - 1) for i in range(3) for j in range(3)]
+TAPS_1x3 = [(0, -1), (0, 0), (0, 1)]
+TAPS_1x1 = [(0, 0)]
+TAPS_FLAT8 = [(f, 0) for f in range(8)]
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _lib_loaded(built_lib):
+    assert torch.cuda.is_available()
+    yield
+
+
+def _fbcrnn_pair():
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import weak_label
+    ora = OM.build_fbcrnn(seed=0)
+    model = weak_label.CRNN.from_config_dict(config.fbcrnn_config())
+    model.load_state_dict(ora.state_dict())
+    model.to(DEV)
+    model.emit_buffers = False
+    return ora, model
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_full_size_fbcrnn_batch32_train_step_vs_oracle(ragged):
+    """BASELINE configs[1] as benchmarked: the reference's default FBCRNN (3.49 M parameters), B = 32 clips
+    of 10 s, raw audio in.  Frame logits within 1e-3 max-abs of the CPU oracle on every valid frame
+    (BASELINE.json north_star), loss |delta| < 1e-4, gradient norm 1e-3 relative, EVERY parameter gradient
+    within 1e-3 of its tensor's largest entry (+ 1e-6 absolute: conv biases in front of a batch norm have
+    a mathematically zero gradient).  ragged: sorted, unequal clip lengths as data.collate produces."""
+    from pb_sed_b200 import train
+    ora, model = _fbcrnn_pair()
+    B = 32
+    seq_len = None
+    if ragged:
+        seq_len = sorted([500] * 9 + [int(v) for v in np.linspace(499, 131, B - 9)], reverse=True)
+    batch = OM.synthetic_batch(B, seed=21, seq_len=seq_len)
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'stft'}
+    opt = train.Adam(model, lr=5e-4)
+    model.train()
+    out = model(dict(gb))
+    loss = model.review(gb, out)['loss']
+    loss.backward()
+    torch.cuda.synchronize()
+    z_fwd, z_bwd = model._z_fwd.detach().cpu(), model._z_bwd.detach().cpu()
+    grads = ref_layout_grads(model)           # before the fused Adam zeroes the arena
+    gnorm = opt.step()
+    cb = {k: v for k, v in batch.items() if k != 'audio_data'}
+    ora.train()
+    zr_fwd, zr_bwd, *_ = ora.logits(cb)
+    ora2 = OM.build_fbcrnn(seed=0)
+    ref_loss, ref_gnorm, _ = OM.train_step(ora2, OM.make_adam(ora2), cb)
+    mask = P.compute_mask(zr_fwd, None if seq_len is None else np.array(seq_len), 0, -1)
+    d_fwd = maxdiff(z_fwd.transpose(1, 2) * mask, zr_fwd.detach() * mask)
+    d_bwd = maxdiff(z_bwd.transpose(1, 2) * mask, zr_bwd.detach() * mask)
+    print(f'B=32 ragged={ragged}: logit max|d| fwd {d_fwd:.2e} bwd {d_bwd:.2e}, loss {float(loss):.6f} vs '
+          f'{float(ref_loss):.6f}, grad norm {float(gnorm):.6f} vs {float(ref_gnorm):.6f}')
+    assert d_fwd < 1e-3 and d_bwd < 1e-3, (d_fwd, d_bwd)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4
+    assert abs(float(gnorm) - float(ref_gnorm)) < 1e-3 * float(ref_gnorm)
+    worst = 0.
+    for k, p in ora2.named_parameters():
+        tol = 1e-3 * float(p.grad.abs().max()) + 1e-6
+        d = maxdiff(grads[k], p.grad)
+        worst = max(worst, d / tol)
+        assert d < tol, (k, d, tol)
+    print(f'worst parameter-gradient error / tolerance: {worst:.3f}')
+
+
+# every conv / projection launch of the B = 32 step: (F, Cin, Cout, taps, per_f flatten)
+STEP_LAYERS = [
+    (128, 16, 16, TAPS_3x3), (64, 16, 32, TAPS_3x3), (64, 32, 32, TAPS_3x3), (32, 32, 64, TAPS_3x3),
+    (32, 64, 64, TAPS_3x3), (16, 64, 128, TAPS_3x3), (16, 128, 128, TAPS_3x3), (8, 128, 256, TAPS_3x3),
+    (1, 256, 256, TAPS_1x3), (1, 256, 256, TAPS_1x1), (1, 256, 768, TAPS_1x1),
+]
+
+
+@pytest.mark.parametrize('F,Cin,Cout,taps', STEP_LAYERS)
+def test_step_layer_shapes_batch32_tc_vs_ffma(F, Cin, Cout, taps):
+    """forward (norm + ReLU + ragged mask + fused statistics), data gradient (ReLU-mask epilogue + fused
+    batch-norm-backward sums) and weight gradient of every layer shape of the B = 32 train step: the
+    tensor-core kernels (whatever tile shape / CTA pairing the library picks at this size) against the
+    exact-fp32 FFMA kernels on identical inputs.  3xTF32 keeps ~21 mantissa bits: 2e-5 / 5e-5 relative."""
+    from pb_sed_b200 import ops
+    B, T = 32, 500
+    torch.manual_seed(F + Cin + Cout)
+    x = torch.randn(B, F, T, Cin, device=DEV)
+    W = torch.randn(len(taps), Cout, Cin, device=DEV) / np.sqrt(Cin * len(taps))
+    bias = torch.randn(Cout, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    sl = np.array(sorted([T] * 10 + [int(v) for v in np.linspace(T - 1, 77, B - 10)], reverse=True))
+    seq = ops.SeqLen.make(sl, B, T, DEV)
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, F, F, T, Cin, Cout, taps, relu=True, precision=prec)
+        stats = torch.zeros(Cout, 2, device=DEV, dtype=torch.float64)
+        y = ops.tapgemm(x, W, bias, desc, scale, shift, seq, out_stats=stats)
+        res.append((y, stats))
+    assert reldiff(res[1][0], res[0][0]) < 2e-5
+    assert reldiff(res[1][1], res[0][1]) < 1e-6           # fused batch statistics (fp64 accumulators)
+    # data gradient: dz (B,F,T,Cout) -> g (B,F,T,Cin), ReLU mask of the layer input, norm-backward sums
+    dz = torch.randn(B, F, T, Cout, device=DEV)
+    mean = torch.randn(Cin, device=DEV) * .1
+    rstd = torch.rand(Cin, device=DEV) + .5
+    rtaps = [(-a, -b) for a, b in taps]
+    res = []
+    for prec in (0, 1):
+        ddesc = ops.make_desc(B, F, F, T, Cout, Cin, rtaps, transpose_w=True, precision=prec)
+        sums = torch.zeros(Cin, 2, device=DEV, dtype=torch.float64)
+        g = ops.tapgemm(dz, W, None, ddesc, None, None, seq, ep_src=x, ep_scale=scale, ep_shift=shift,
+                        ep_mean=mean, ep_rstd=rstd, ep_sums=sums)
+        res.append((g, sums))
+    assert reldiff(res[1][0], res[0][0]) < 2e-5
+    assert reldiff(res[1][1], res[0][1]) < 1e-5
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, F, F, T, Cin, Cout, taps, relu=True, precision=prec)
+        dW = torch.zeros(len(taps), Cout, Cin, device=DEV)
+        db = torch.zeros(Cout, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, db, scale, shift, seq, mask_out=False)
+        res.append((dW, db))
+    assert reldiff(res[1][0], res[0][0]) < 5e-5
+    assert reldiff(res[1][1], res[0][1]) < 5e-5
+
+
+def test_flatten_layer_batch32_tc_vs_ffma():
+    """first cnn_1d layer at B = 32: 8 frequency taps over the (B,8,T,256) map, per-(f,c) batch norm, and its
+    transposed data gradient (F 1 -> 8, one valid tap per output row)."""
+    from pb_sed_b200 import ops
+    B, Fh, T, Cin, Cout = 32, 8, 500, 256, 256
+    torch.manual_seed(5)
+    x = torch.randn(B, Fh, T, Cin, device=DEV)
+    W = torch.randn(Fh, Cout, Cin, device=DEV) / np.sqrt(Cin * Fh)
+    scale = torch.rand(Fh * Cin, device=DEV) + .5
+    shift = torch.randn(Fh * Cin, device=DEV) * .3
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, Fh, 1, T, Cin, Cout, TAPS_FLAT8, relu=True, per_f=True, precision=prec)
+        res.append(ops.tapgemm(x, W, None, desc, scale, shift, None))
+    assert reldiff(res[1], res[0]) < 2e-5
+    dz = torch.randn(B, 1, T, Cout, device=DEV)
+    res = []
+    for prec in (0, 1):
+        ddesc = ops.make_desc(B, 1, Fh, T, Cout, Cin, [(-f, 0) for f in range(Fh)], per_f=True,
+                              transpose_w=True, precision=prec)
+        res.append(ops.tapgemm(dz, W, None, ddesc, None, None, None, ep_src=x, ep_scale=scale, ep_shift=shift))
+    assert reldiff(res[1], res[0]) < 2e-5
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, Fh, 1, T, Cin, Cout, TAPS_FLAT8, relu=True, per_f=True, precision=prec)
+        dW = torch.zeros(Fh, Cout, Cin, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, None, scale, shift, None, mask_out=False)
+        res.append(dW)
+    assert reldiff(res[1], res[0]) < 5e-5
+
+
+@pytest.mark.parametrize('B,bidir,In', [(32, False, 256), (33, False, 256), (64, True, 266)])
+def test_gru_h256_bench_batch_vs_torch(B, bidir, In):
+    """the H = 256 recurrence at the benchmark's batch sizes: B = 32 -> clusters of 5 clips with a 2-clip
+    tail, B = 33 -> a 3-clip tail; B = 64 bidirectional with the 266-wide tag-conditioned input of the BiCRNN.
+    Forward + input / parameter gradients against torch.nn.GRU on the CPU, ragged lengths."""
+    from pb_sed_b200 import modules as M
+    torch.manual_seed(B)
+    T, H, K = 120, 256, 10
+    out_kw = dict(out_channels=[256, K], kernel_size=1, norm='batch', norm_kwargs={'eps': 1e-3})
+    gru = torch.nn.GRU(In, H, num_layers=2, batch_first=True, bidirectional=bidir)
+    ora = P.GRU(gru, P.CNN1d(H * (2 if bidir else 1), **out_kw, pre_activation=False, output_layer=True),
+                reverse=not bidir).train()
+    prod = M.GRU(dict(input_size=In, hidden_size=H, num_layers=2, bidirectional=bidir), out_kw, reverse=not bidir)
+    prod.load_state_dict(ora.state_dict())
+    prod.to(DEV).train()
+    sl = np.array(sorted([T] * 7 + [int(v) for v in np.linspace(T - 1, 3, B - 7)], reverse=True))
+    x = torch.randn(B, In, T)
+    xr = x.clone().requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    y_ref, _ = ora(xr, sl)
+    y, _ = prod(xg, sl)
+    mask = P.compute_mask(y_ref, sl, 0, -1)
+    assert maxdiff(y.cpu() * mask, y_ref * mask) < 2e-4
+    g = torch.randn_like(y_ref) * mask
+    y_ref.backward(g)
+    y.backward(g.to(DEV))
+    xmask = P.compute_mask(x, sl, 0, -1)
+    assert maxdiff(xg.grad.cpu() * xmask, xr.grad * xmask) < 2e-4 * max(1., float(xr.grad.abs().max()))
+    grads = ref_layout_grads(prod)
+    for k, p in ora.named_parameters():
+        assert maxdiff(grads[k], p.grad) < 5e-4 * max(1., float(p.grad.abs().max())), k
+
+
+def test_full_size_bicrnn_batch64_scores_vs_oracle():
+    """BASELINE configs[3] shape: full-size tag-conditioned BiCRNN (2-layer bidirectional GRU, H = 256,
+    266-wide input), B = 64, eval mode, raw audio in.  Frame logits within 1e-3 of the CPU oracle, scores
+    within 1e-4; then one train-mode forward + loss."""
+    from pb_sed_b200 import config
+    from pb_sed_b200.models import strong_label
+    B = 64
+    ora = OM.build_bicrnn(seed=0)
+    model = strong_label.CRNN.from_config_dict(config.bicrnn_config())
+    model.load_state_dict(ora.state_dict())
+    model.to(DEV)
+    batch = OM.synthetic_batch(16, seed=31)
+    rep = B // 16
+    tag = (batch['weak_targets'] > .5)
+    seq_len = sorted([500] * 40 + [int(v) for v in np.linspace(499, 200, B - 40)], reverse=True)
+    cb = dict(stft=batch['stft'].repeat(rep, 1, 1, 1, 1), tag_condition=tag.repeat(rep, 1), seq_len=seq_len,
+              weak_targets=batch['weak_targets'].repeat(rep, 1),
+              strong_targets=batch['boundary_targets'].repeat(rep, 1, 1))
+    gb = dict(audio_data=batch['audio_data'].repeat(rep, 1, 1).to(DEV), tag_condition=cb['tag_condition'].to(DEV),
+              seq_len=seq_len, weak_targets=cb['weak_targets'].to(DEV), strong_targets=cb['strong_targets'].to(DEV))
+    ora.eval(); model.eval()
+    with torch.no_grad():
+        z_ref, sl, _ = ora.logits(cb)
+        y_ref, _ = ora.sound_event_detection(cb)
+        y, _ = model.sound_event_detection(dict(gb))
+        z = model._z.detach().cpu()
+    mask = P.compute_mask(z_ref, np.array(seq_len), 0, -1)
+    d = maxdiff(z.transpose(1, 2) * mask, z_ref * mask)
+    print(f'BiCRNN B=64 eval: logit max|d| {d:.2e}')
+    assert d < 1e-3
+    assert maxdiff(y.cpu(), y_ref) < 1e-4
+    ora.train(); model.train()
+    out = model(dict(gb))
+    loss = model.review(gb, out)['loss']
+    ref_out = ora(cb)
+    ref_loss = ora.review(cb, ref_out)['loss']
+    assert abs(float(loss) - float(ref_loss)) < 2e-4 * max(1., abs(float(ref_loss)))

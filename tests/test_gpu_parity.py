@@ -510,19 +510,54 @@ def test_freeze_stops_gradients_of_the_first_layers():
     no gradient, the rest match the unfrozen run."""
     ora, prod = tiny_pair(seed=5)
     _, ref = tiny_pair(seed=5)
-    prod.cnn.cnn_2d.freeze(2)
+    prod.cnn.cnn_2d.freeze(2, freeze_norm_stats=False)      # batch statistics stay live: only the gradients stop
     batch = OM.synthetic_batch(4, num_samples=645, stft_kwargs=TINY_STFT, seed=5)
     gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'audio_data'}
     for m in (prod, ref):
         m.train()
         m.review(gb, m(dict(gb)))['loss'].backward()
     for (n, p), (_, q) in zip(prod.named_parameters(), ref.named_parameters()):
-        frozen = n.startswith('cnn.cnn_2d.convs.0') or n.startswith('cnn.cnn_2d.convs.1') or \
-            n.startswith('cnn.cnn_2d.norms.1')
+        frozen = n.startswith('cnn.cnn_2d.convs.0.') or n.startswith('cnn.cnn_2d.convs.1.')
         if frozen:
             assert not p.requires_grad and p.grad is None, n
         else:
             assert p.grad is not None and maxdiff(p.grad, q.grad) < 1e-5 * max(1., float(q.grad.abs().max())), n
+
+
+def test_freeze_norm_stats_uses_running_statistics_in_train_mode():
+    """freeze(n, freeze_norm_stats=True) -- the reference experiments' default (training.py:343-350): the frozen
+    layers normalise with their RUNNING statistics in train mode and leave them untouched; scores, loss and
+    the gradients of the live layers match the oracle frozen the same way."""
+    ora, prod = tiny_pair(seed=6)
+    batch = OM.synthetic_batch(4, num_samples=645, stft_kwargs=TINY_STFT, seed=6, seq_len=[41, 40, 33, 17])
+    gb = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items() if k != 'audio_data'}
+    cb = {k: v for k, v in batch.items() if k != 'audio_data'}
+    for m, b in ((ora, cb), (prod, gb)):          # one live step so that the running statistics are not the init values
+        m.train()
+        m(dict(b))
+    for m in (ora, prod):
+        m.cnn.cnn_2d.freeze(2, freeze_norm_stats=True)
+        m.cnn.cnn_1d.freeze(1, freeze_norm_stats=True)
+    before = {k: v.clone() for k, v in prod.state_dict().items() if 'running' in k or 'num_tracked' in k}
+    out_r = ora(dict(cb))
+    ora.review(cb, out_r)['loss'].backward()
+    out = prod(dict(gb))
+    loss = prod.review(gb, out)['loss']
+    loss.backward()
+    mask = P.compute_mask(out_r[0], np.array(batch['seq_len']), 0, -1)
+    assert maxdiff(out[0].cpu() * mask, out_r[0] * mask) < 1e-4
+    after = prod.state_dict()
+    for k, v in before.items():
+        frozen = any(k.startswith(f'cnn.cnn_2d.convs.{i}.') for i in (0, 1)) or k.startswith('cnn.cnn_1d.convs.0.')
+        if frozen:
+            assert torch.equal(after[k], v), k                    # frozen statistics did not move
+    for k, v in ora.state_dict().items():
+        if 'running' in k or 'num_tracked' in k:
+            assert maxdiff(after[k], v) < 1e-4 * max(1., float(v.abs().max())), k
+    grads = ref_layout_grads(prod)
+    for k, p in ora.named_parameters():
+        if p.requires_grad:
+            assert maxdiff(grads[k], p.grad) < 5e-4 * max(1., float(p.grad.abs().max())), k
 
 
 def test_device_loader_double_buffers_pinned_batches():
@@ -568,7 +603,7 @@ def test_reference_doctest_contract_weak_label_crnn():
     review['loss'].backward()
     g = [p.grad for p in crnn.parameters() if p.grad is not None]
     assert len(g) > 10 and all(torch.isfinite(x).all() for x in g)
-    assert float(crnn.cnn.cnn_1d.convs[0].weight.grad.abs().max()) > 0        # gradient reaches the flatten conv
+    assert float(crnn.cnn.cnn_1d.convs[0].conv.weight.grad.abs().max()) > 0        # gradient reaches the flatten conv
     crnn.eval()
     with torch.no_grad():
         assert crnn.tagging({**inputs})[0].shape == (4, 10, 1)

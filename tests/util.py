@@ -1,6 +1,7 @@
 """shared helpers for the parity tests (the oracle is the checker; see oracle/__init__.py)."""
 import copy
 import os
+import re
 
 import numpy as np
 import torch
@@ -9,9 +10,16 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 TINY_STFT = dict(shift=16, window_length=48, size=64)
 
 
+def padertorch_key(k):
+    """the golden files were frozen with a flat ``convs.<i>.{weight,bias}`` / ``norms.<i>.*`` key layout; the
+    modules (and padertorch checkpoints) nest them as ``convs.<i>.conv.*`` / ``convs.<i>.norm.*``."""
+    k = re.sub(r'convs\.(\d+)\.(weight|bias)$', r'convs.\1.conv.\2', k)
+    return re.sub(r'norms\.(\d+)\.', r'convs.\1.norm.', k)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + '.npz'))
-    d = {k: z[k] for k in z.files}
+    d = {padertorch_key(k): z[k] for k in z.files if not k.endswith('feature_extractor.fbanks')}
     state = {k[len('state.'):]: torch.from_numpy(v) for k, v in d.items() if k.startswith('state.')}
     grads = {k[len('grad.'):]: torch.from_numpy(v) for k, v in d.items() if k.startswith('grad.')}
     return d, state, grads
