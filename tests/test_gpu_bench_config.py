@@ -45,7 +45,7 @@ def test_full_size_fbcrnn_batch32_train_step_vs_oracle(ragged):
     (BASELINE.json north_star), loss |delta| < 1e-4, gradient norm 1e-3 relative, EVERY parameter gradient
     within 1e-3 of its tensor's largest entry (+ 1e-6 absolute: conv biases in front of a batch norm have
     a mathematically zero gradient).  ragged: sorted, unequal clip lengths as data.collate produces."""
-    from pb_sed_b200 import train
+    from pb_sed_b200 import train, ops
     ora, model = _fbcrnn_pair()
     B = 32
     seq_len = None
@@ -57,10 +57,22 @@ def test_full_size_fbcrnn_batch32_train_step_vs_oracle(ragged):
     model.train()
     out = model(dict(gb))
     loss = model.review(gb, out)['loss']
-    loss.backward()
+    # keep the operands of the first layer's weight gradient (Cin = 1) for the float64 check below
+    captured, real_wgrad = {}, ops.tapgemm_wgrad
+
+    def spy(x, dout, desc, dW, dbias, *a, **kw):
+        if desc.Cin == 1:
+            captured['x'], captured['dz'] = x.detach().clone(), dout.detach().clone()
+        return real_wgrad(x, dout, desc, dW, dbias, *a, **kw)
+    ops.tapgemm_wgrad = spy
+    try:
+        loss.backward()
+    finally:
+        ops.tapgemm_wgrad = real_wgrad
     torch.cuda.synchronize()
     z_fwd, z_bwd = model._z_fwd.detach().cpu(), model._z_bwd.detach().cpu()
     grads = ref_layout_grads(model)           # before the fused Adam zeroes the arena
+    got = model.cnn.cnn_2d.convs[0].conv.weight.grad.detach().clone()          # native (taps, Cout, 1)
     gnorm = opt.step()
     cb = {k: v for k, v in batch.items() if k != 'audio_data'}
     ora.train()
@@ -76,12 +88,29 @@ def test_full_size_fbcrnn_batch32_train_step_vs_oracle(ragged):
     assert abs(float(loss) - float(ref_loss)) < 1e-4
     assert abs(float(gnorm) - float(ref_gnorm)) < 1e-3 * float(ref_gnorm)
     worst = 0.
+    L0 = 'cnn.cnn_2d.convs.0.conv.weight'
     for k, p in ora2.named_parameters():
-        tol = 1e-3 * float(p.grad.abs().max()) + 1e-6
+        # the first conv's weight gradient is the one ill-conditioned sum of the step: 2 M products of the
+        # zero-mean batch-norm gradient with the +-6 features cancel to ~1e-3 of their absolute sum, so the
+        # fp32 rounding of the upstream gradient (1e-5 relative on BOTH sides) shows up at the 1e-2 level of the
+        # result; it gets 3e-2 here and an exact check of the kernel itself below
+        tol = (3e-2 if k == L0 else 1e-3) * float(p.grad.abs().max()) + 1e-6
         d = maxdiff(grads[k], p.grad)
-        worst = max(worst, d / tol)
+        if k != L0:
+            worst = max(worst, d / tol)
         assert d < tol, (k, d, tol)
     print(f'worst parameter-gradient error / tolerance: {worst:.3f}')
+    # first-layer weight gradient: the kernel against a float64 evaluation of the same sum on the same operands
+    x64, dz64 = captured['x'].double(), captured['dz'].double()      # (B,F,T,1), (B,F,T,16)
+    xp = torch.nn.functional.pad(x64[..., 0], (1, 1, 1, 1))
+    F_, T_ = x64.shape[1], x64.shape[2]
+    ref = torch.stack([(dz64 * xp[:, 1 + df:1 + df + F_, 1 + dt:1 + dt + T_, None]).sum((0, 1, 2))
+                       for df in (-1, 0, 1) for dt in (-1, 0, 1)])                # (9, 16) = native (taps, Cout)
+    absum = torch.stack([(dz64 * xp[:, 1 + df:1 + df + F_, 1 + dt:1 + dt + T_, None]).abs().sum((0, 1, 2))
+                         for df in (-1, 0, 1) for dt in (-1, 0, 1)])
+    print(f'L0 weight gradient: max|g| {float(ref.abs().max()):.3e}, sum of |terms| {float(absum.max()):.3e}, '
+          f'kernel vs float64 {maxdiff(got[:, :, 0], ref):.2e}, oracle vs GPU {maxdiff(grads[L0], ora2.get_parameter(L0).grad):.2e}')
+    assert maxdiff(got[:, :, 0], ref) < 2e-6 * float(absum.max())       # fp32 accumulation of the kernel itself
 
 
 # every conv / projection launch of the B = 32 step: (F, Cin, Cout, taps, per_f flatten)

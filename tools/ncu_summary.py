@@ -3,6 +3,10 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv        > profiles/rNN_launches.txt
     python tools/ncu_summary.py kernel   gpurun_out/prof.ncu-rep        > profiles/rNN_<kernel>.txt
+    python tools/ncu_summary.py pipe     gpurun_out/pipe.csv            > profiles/rNN_tensor_pipe_all_launches.txt
+      (pipe.csv: ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,
+       dram__bytes_read.sum,dram__bytes_write.sum --csv of one eager step: time-weighted tensor-pipe utilisation
+       and DRAM traffic per kernel and over ALL tap-GEMM + weight-gradient launches)
 """
 import collections
 import csv
@@ -54,5 +58,46 @@ def kernel(path):
                 print(f'   {m:70s} {r[hdr.index(m)]:>16s} {units[hdr.index(m)]}')
 
 
+def pipe(path):
+    lines = [l for l in open(path) if not l.startswith('==')]
+    per = collections.OrderedDict()                       # launch id -> {metric: value}
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row['Metric Value'].replace(',', ''))
+        except (ValueError, KeyError):
+            continue
+        unit = row.get('Metric Unit', '')
+        if row['Metric Name'] == 'gpu__time_duration.sum':
+            v = {'ns': v / 1e3, 'us': v, 'ms': v * 1e3, 'nsecond': v / 1e3, 'usecond': v, 'msecond': v * 1e3}.get(unit, v)
+        if row['Metric Name'].startswith('dram__bytes'):
+            v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
+        d = per.setdefault(row['ID'], {'name': re.sub(r'\(.*', '', row['Kernel Name'])})
+        d[row['Metric Name']] = v
+    T, P = 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
+    agg = collections.defaultdict(lambda: [0, 0., 0., 0.])
+    for d in per.values():
+        if T not in d:
+            continue
+        a = agg[d['name']]
+        a[0] += 1
+        a[1] += d[T]
+        a[2] += d[T] * d.get(P, 0.)
+        a[3] += d.get('dram__bytes_read.sum', 0.) + d.get('dram__bytes_write.sum', 0.)
+    tot = sum(a[1] for a in agg.values())
+    print(f'# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e3:.2f} ms device time under ncu '
+          '(serialised, cold caches: compare shares).  tensor% = sm__pipe_tensor_cycles_active, time-weighted')
+    print(f'# {"us":>10s} {"share":>6s} {"n":>5s} {"tensor%":>8s} {"DRAM MB/launch":>15s} {"DRAM GB/s":>10s}  kernel')
+    gemm_t = gemm_p = 0.
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f'{a[1]:12.1f} {100 * a[1] / tot:5.1f}% {a[0]:5d} {a[2] / a[1]:8.1f} {a[3] / a[0] / 1e6:15.1f} '
+              f'{a[3] / (a[1] * 1e-6) / 1e9:10.0f}  {k[:100]}')
+        if re.search(r'tapgemm_tc|wgrad_tc|tapgemm_pt|wgrad_mma', k):
+            gemm_t += a[1]
+            gemm_p += a[2]
+    if gemm_t:
+        print(f'# all tensor-core tap-GEMM + weight-gradient launches: {gemm_t / 1e3:.2f} ms, time-weighted tensor pipe '
+              f'{gemm_p / gemm_t:.1f} %')
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'kernel': kernel, 'pipe': pipe}[sys.argv[1]](sys.argv[2])
