@@ -273,6 +273,27 @@ norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, 
   }
 }
 
+// dx = A[c] * g + Bx[c] * x + C0[c] on valid rows (0 behind the clip end), with
+//   A = gamma*rstd,  Bx = -A*rstd*s1/n,  C0 = -A*s0/n - Bx*mean      (s0 = sum g, s1 = sum g*xhat)
+// The grid stride is a multiple of C/4, so a thread keeps its channel quad: the coefficients live in registers
+// (recomputed only when the frequency row changes in the per-(f,c) case) and the loop body is 2 loads + 1 store
+// per 16 output bytes, four rows in flight per thread.
+struct NbaCoef { float4 a, bx, c0; };
+__device__ __forceinline__ NbaCoef nba_coef(const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                            const float4* __restrict__ gamma, const double* __restrict__ sums,
+                                            float inv_n, int i4) {
+  const float4 rs = __ldg(rstd + i4), mu = __ldg(mean + i4);
+  const float4 ga = gamma ? __ldg(gamma + i4) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const double* sp = sums + 8 * (long long)i4;
+  NbaCoef k;
+  k.a = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+  k.bx = make_float4(-k.a.x * rs.x * ((float)sp[1] * inv_n), -k.a.y * rs.y * ((float)sp[3] * inv_n),
+                     -k.a.z * rs.z * ((float)sp[5] * inv_n), -k.a.w * rs.w * ((float)sp[7] * inv_n));
+  k.c0 = make_float4(-k.a.x * ((float)sp[0] * inv_n) - k.bx.x * mu.x, -k.a.y * ((float)sp[2] * inv_n) - k.bx.y * mu.y,
+                     -k.a.z * ((float)sp[4] * inv_n) - k.bx.z * mu.z, -k.a.w * ((float)sp[6] * inv_n) - k.bx.w * mu.w);
+  return k;
+}
+
 __global__ void __launch_bounds__(256)
 norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ x, int F, int T, int C4,
                        int per_f, const int* __restrict__ seq_len, const float4* __restrict__ mean,
@@ -280,26 +301,47 @@ norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ 
                        const double* __restrict__ sums, float inv_n, float4* __restrict__ dx,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch) {
   if (inv_n <= 0.f) inv_n = (float)(1.0 / sums[2 * nch]);   // device-side count
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-    const int q = (int)(i % C4);
-    const long long row = i / C4;
-    const int t = (int)(row % T);
-    const long long gq = row / T;
-    const int f = (int)(gq % F), b = (int)(gq / F);
-    const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < len_b) {
-      const int i4 = (per_f ? f * C4 : 0) + q;
-      const float4 rs = __ldg(rstd + i4), mu = __ldg(mean + i4), xv = __ldg(x + i), gv = __ldg(g + i);
-      const float4 ga = gamma ? __ldg(gamma + i4) : make_float4(1.f, 1.f, 1.f, 1.f);
-      const double* sp = sums + 8 * (long long)i4;
-      r.x = ga.x * rs.x * (gv.x - (float)sp[0] * inv_n - (xv.x - mu.x) * rs.x * ((float)sp[1] * inv_n));
-      r.y = ga.y * rs.y * (gv.y - (float)sp[2] * inv_n - (xv.y - mu.y) * rs.y * ((float)sp[3] * inv_n));
-      r.z = ga.z * rs.z * (gv.z - (float)sp[4] * inv_n - (xv.z - mu.z) * rs.z * ((float)sp[5] * inv_n));
-      r.w = ga.w * rs.w * (gv.w - (float)sp[6] * inv_n - (xv.w - mu.w) * rs.w * ((float)sp[7] * inv_n));
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;       // multiple of C4 (256 % C4 == 0)
+  const int q = (int)(gtid % C4);
+  const long long rstep = stride / C4, rows = total4 / C4;
+  constexpr int U = 4;
+  int f_cur = -1;
+  NbaCoef k;
+  if (!per_f) k = nba_coef(mean, rstd, gamma, sums, inv_n, q);
+  for (long long row0 = gtid / C4; row0 < rows; row0 += U * rstep) {
+    float4 gv[U], xv[U];
+    bool ok[U];
+    int fr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * rstep;
+      ok[u] = false;
+      fr[u] = 0;
+      if (row < rows) {
+        const int t = (int)(row % T);
+        const long long gq = row / T;
+        fr[u] = (int)(gq % F);
+        const int b = (int)(gq / F);
+        const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
+        ok[u] = t < len_b;
+        if (ok[u]) { gv[u] = __ldg(g + row * C4 + q); xv[u] = __ldg(x + row * C4 + q); }
+      }
     }
-    dx[i] = r;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * rstep;
+      if (row >= rows) break;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        if (per_f && fr[u] != f_cur) { f_cur = fr[u]; k = nba_coef(mean, rstd, gamma, sums, inv_n, f_cur * C4 + q); }
+        r.x = fmaf(k.a.x, gv[u].x, fmaf(k.bx.x, xv[u].x, k.c0.x));
+        r.y = fmaf(k.a.y, gv[u].y, fmaf(k.bx.y, xv[u].y, k.c0.y));
+        r.z = fmaf(k.a.z, gv[u].z, fmaf(k.bx.z, xv[u].z, k.c0.z));
+        r.w = fmaf(k.a.w, gv[u].w, fmaf(k.bx.w, xv[u].w, k.c0.w));
+      }
+      dx[row * C4 + q] = r;
+    }
   }
   if (blockIdx.x == 0 && dgamma) {
     for (int j = threadIdx.x; j < nch; j += blockDim.x) {
@@ -319,11 +361,11 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
   const float inv_count = count > 0. ? (float)(1.0 / count) : 0.f;   // <= 0: count = sums[2*nch] on the device
   const long long total = (long long)B * F * T * C;
   const int nch = per_f ? F * C : C;
-  if ((C & 3) == 0 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
+  if ((C & 3) == 0 && 256 % (C / 4) == 0 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
                         ((uintptr_t)save_rstd) | ((uintptr_t)gamma)) & 15) == 0) {
     const long long total4 = total / 4;
     int blocks4 = (int)((total4 + 255) / 256);
-    if (blocks4 > 148 * 16) blocks4 = 148 * 16;
+    if (blocks4 > 148 * 8) blocks4 = 148 * 8;
     norm_bwd_apply4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x), F, T, C / 4, per_f, seq_len,
         reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),

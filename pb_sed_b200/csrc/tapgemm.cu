@@ -216,6 +216,10 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
                         const float* ep_rstd, double* ep_sums, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled);
 
+int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale, const float* shift,
+                        const int* seq_len, const float* W, const float* bias, float* out, const float* ep_src,
+                        const float* ep_scale, const float* ep_shift, void* workspace, long long ws_bytes,
+                        cudaStream_t st, int* handled);
 int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                            const float* shift, const int* seq_len, const float* W, const float* bias,
                            float* out, const float* ep_src, cudaStream_t st, int* handled);
@@ -260,14 +264,23 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   if ((out_stats || ep_sums) && p.out_stride != p.Cout) return PBSED_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int* load_seq = d->no_input_mask ? nullptr : seq_len;
+  int fw_done = 0;
   if (d->precision != 0) {
-    int handled = 0;
-    rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
-                             out_stats, ep_mean, ep_rstd, ep_sums, workspace, workspace_bytes, st, &handled);
-    if (handled || rc) return rc;
+    // narrow 3x3 layers: the frequency-walking persistent kernel (no fused column sums: separate passes below)
+    rc = tapgemm_fw_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
+                             workspace, workspace_bytes, st, &fw_done);
+    if (rc) return rc;
+    if (!fw_done) {
+      int handled = 0;
+      rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
+                               out_stats, ep_mean, ep_rstd, ep_sums, workspace, workspace_bytes, st, &handled);
+      if (handled || rc) return rc;
+    }
   }
-  rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
-  if (rc) return rc;
+  if (!fw_done) {
+    rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
+    if (rc) return rc;
+  }
   // kernels without fused reductions: run them as separate passes over the finished map
   if (out_stats) {
     rc = pbsed_channel_stats(out, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, out_stats, stream);

@@ -1,0 +1,361 @@
+// tapgemm_fw.cu -- "frequency-walking" tcgen05 tap-GEMM for the NARROW 3x3 conv layers (16 / 32 channels)
+// of the CNN2d stack (padertorch CNN2d layer bodies, pb_sed/experiments/weak_label_crnn/training.py:158-169,
+// 218-230: layers 16->16 @ F128, 16->32 @ F64, 32->32 @ F64) and their data gradients.
+//
+// Why a second kernel: with N = Cout = 16 the generic kernel (tapgemm_tc.cu) issues M128 x N16 x K8 MMAs whose
+// A-operand fetch (4 KB of shared memory per instruction) bounds the tensor pipe at 1/4 of its rate, re-reads
+// every input row for three output rows, and runs 16 k short-lived CTAs whose load -> convert -> MMA -> epilogue
+// chain never overlaps itself (measured r02: 277 us for 262 MB of algorithmic traffic, DRAM at 15 %, tensor pipe
+// at 14 %).  Here one PERSISTENT CTA per SM walks the frequency axis of a (clip, 128-frame) tile:
+//   * every input strip (row f, 130 frames incl. halo, 16 channels) is fetched ONCE -- by tensor-map TMA
+//     (cp.async.bulk.tensor) into an 8-deep raw ring -- converted once (norm + ReLU + mask + hi/lo split) and
+//     feeds the THREE output rows f-1, f, f+1 with one MMA per time tap: the weights of df = +1 / 0 / -1 are
+//     stacked along N (N = 3 x Cout = 48 / 96), the three rows' accumulators are adjacent TMEM columns;
+//   * a whole layer's weight image (<= 72 KB incl. hi/lo) stays resident in shared memory;
+//   * accumulators for R = 256 / Cout output rows live in one half of TMEM, the other half belongs to the
+//     neighbouring work item, so the epilogue (TMEM -> registers -> bias / ReLU-mask -> 64-byte row stores)
+//     of finished rows overlaps the MMAs of the next rows and of the next item; drained columns are re-zeroed
+//     by the epilogue (tcgen05.st), so every MMA accumulates.
+// Same arithmetic as tapgemm_tc.cu (3xTF32 split or one TF32 pass, fp32 accumulation), same tap-GEMM contract
+// (include/pbsed_b200.h); fused column sums are left to the caller's separate passes.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
+
+namespace {
+
+constexpr int FW_TM = 128;                 // frames per tile (= MMA M)
+constexpr int FW_ROWS = FW_TM + 2;         // strip rows incl. one halo frame each side
+constexpr int FW_KB = 16, FW_KCH = 4;      // channels / 16-byte chunks per stage
+constexpr int FW_NA = 3;                   // converted operand stages
+constexpr int FW_NRAW = 8;                 // raw (TMA) stages
+constexpr int FW_MAXR = 16;                // output rows per TMEM half (Cout = 16)
+constexpr uint32_t FW_A_LBO = FW_ROWS * 16;
+constexpr uint32_t FW_A_PART = FW_KCH * FW_A_LBO;      // 8320 B: one hi (or lo) strip stage
+constexpr uint32_t FW_A_STAGE = 2 * FW_A_PART;
+constexpr uint32_t FW_RAW_STAGE = FW_ROWS * FW_KB * 4; // 8320 B
+constexpr int FW_THREADS = 320;            // 4 converter warps, 4 epilogue warps, MMA warp, TMA warp
+
+struct FwParams {
+  int B, F, T, Cin, Cout;
+  int relu, single;
+  int nkb, R;                 // channel blocks of 16; output rows per item (= 256 / Cout)
+  int t_tiles, f_chunks, items;
+  unsigned w_bytes;
+};
+
+struct __align__(16) FwCtl {
+  uint64_t raw_full[FW_NRAW], raw_empty[FW_NRAW], a_full[FW_NA], a_empty[FW_NA];
+  uint64_t acc_full[2][FW_MAXR], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+// weight image: [dt 3][kb][part hi|lo][k-chunk 4][n' = blk * Cout + n][4 floats], blk 0/1/2 <-> df = +1/0/-1,
+// i.e. the output rows f-1, f, f+1 a source strip f contributes to
+__global__ void __launch_bounds__(256)
+fwprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
+              int Cin, int Cout, int t00, int t01, int t02, int t10, int t11, int t12, int t20, int t21, int t22,
+              float* __restrict__ img, int single) {
+  const int tapidx[3][3] = {{t00, t01, t02}, {t10, t11, t12}, {t20, t21, t22}};   // [df+1][dt+1]
+  const int nkb = Cin / FW_KB, N3 = 3 * Cout;
+  const int total = 3 * nkb * FW_KCH * N3 * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 3;
+    int q = i >> 2;
+    const int np = q % N3; q /= N3;
+    const int kc = q % FW_KCH; q /= FW_KCH;
+    const int kb = q % nkb;
+    const int dt = q / nkb;
+    const int blk = np / Cout, n = np - blk * Cout;
+    const int tap = tapidx[2 - blk][dt];                  // df = 1 - blk
+    const int cin = kb * FW_KB + kc * 4 + e;
+    const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)n * w_sn + (long long)cin * w_sc);
+    const float hi = single ? tf32_rn(w) : __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const long long part = (long long)FW_KCH * N3 * 4;
+    const long long base = (long long)(dt * nkb + kb) * 2 * part + ((long long)kc * N3 + np) * 4 + e;
+    img[base] = hi;
+    img[base + part] = w - hi;
+  }
+}
+
+__global__ void __launch_bounds__(FW_THREADS, 1)
+tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const int* __restrict__ seq_len,
+                  const int* __restrict__ load_seq_len, const float* __restrict__ wimg,
+                  const float* __restrict__ bias, float* __restrict__ out, const float* __restrict__ ep_src,
+                  const float* __restrict__ ep_scale, const float* __restrict__ ep_shift) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* w_smem = smem_raw;
+  uint8_t* a_smem = w_smem + p.w_bytes;
+  uint8_t* r_smem = a_smem + FW_NA * FW_A_STAGE;
+  FwCtl* ctl = reinterpret_cast<FwCtl*>(r_smem + FW_NRAW * FW_RAW_STAGE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cout = p.Cout, R = p.R;
+
+  if (tid == 0) {
+    for (int i = 0; i < FW_NRAW; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], 128); }
+    for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
+    for (int h = 0; h < 2; ++h) {
+      for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], 1);
+      mbar_init(&ctl->acc_empty[h], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(&ctl->tmem_base, 512);
+  for (unsigned i = tid; i < p.w_bytes / 16; i += FW_THREADS)          // the layer's weights: resident for the whole kernel
+    reinterpret_cast<float4*>(w_smem)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  if (warp >= 4 && warp < 8) {                // all 512 accumulator columns start at zero: every MMA accumulates
+    for (int col = 0; col < 512; col += 16) tmem_st16_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < 4) {
+    // ============================== converters ==============================
+    const int c = tid & 3, r0 = tid >> 2;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
+      const int fo0 = fc * R, t0 = tt * FW_TM;
+      const int len_in = load_seq_len ? min(__ldg(load_seq_len + b), p.T) : p.T;
+      const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
+      for (int f = f_lo; f <= f_hi; ++f)
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (scale) {
+            sc = __ldg(reinterpret_cast<const float4*>(scale + kb * FW_KB + c * 4));
+            sh = __ldg(reinterpret_cast<const float4*>(shift + kb * FW_KB + c * 4));
+          }
+          const int rs = it % FW_NRAW, slot = it % FW_NA;
+          const float* raw = reinterpret_cast<const float*>(r_smem + rs * FW_RAW_STAGE);
+          uint8_t* hi_base = a_smem + slot * FW_A_STAGE;
+          uint8_t* lo_base = hi_base + FW_A_PART;
+          mbar_wait(&ctl->raw_full[rs], (it / FW_NRAW) & 1);
+          mbar_wait(&ctl->a_empty[slot], ((it / FW_NA) & 1) ^ 1);
+#pragma unroll
+          for (int u = 0; u < (FW_ROWS + 31) / 32; ++u) {
+            const int r = r0 + 32 * u, t = t0 + r - 1;
+            if (r >= FW_ROWS) break;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < len_in) {
+              x = *reinterpret_cast<const float4*>(raw + r * FW_KB + c * 4);
+              if (scale) {
+                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+              }
+              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+            const uint32_t o = (uint32_t)(c * FW_ROWS + r) * 16;
+            if (p.single) {
+              *reinterpret_cast<float4*>(hi_base + o) = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+            } else {
+              float4 h;
+              h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+              h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+              h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+              h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(hi_base + o) = h;
+              *reinterpret_cast<float4*>(lo_base + o) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+          }
+          mbar_arrive(&ctl->raw_empty[rs]);
+          fence_async_smem();
+          mbar_arrive(&ctl->a_full[slot]);
+        }
+    }
+  } else if (warp < 8) {
+    // ============================== epilogue ==============================
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    int li = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+      const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
+      const int fo0 = fc * R, t = tt * FW_TM + row;
+      const int h = li & 1;
+      const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+      const bool in_map = t < p.T;
+      for (int r = 0; r < R; ++r) {
+        const long long orow = ((long long)b * p.F + fo0 + r) * p.T + t;
+        mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
+        tc_fence_after();
+        for (int cc = 0; cc < Cout; cc += 16) {
+          const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(h * 256 + r * Cout + cc);
+          float v[16];
+          tmem_ld16(ta, v);
+          tmem_st16_zero(ta);                          // the column block is free for the item after next
+          if (in_map) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cc + j));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (ep_src) {                              // ReLU / sequence mask of a data-gradient pass
+              float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (t < len_b) {
+                sv = __ldg(reinterpret_cast<const float4*>(ep_src + orow * Cout + cc + j));
+                if (ep_scale) {
+                  const float4 es = __ldg(reinterpret_cast<const float4*>(ep_scale + cc + j));
+                  const float4 eh = __ldg(reinterpret_cast<const float4*>(ep_shift + cc + j));
+                  sv.x = fmaf(sv.x, es.x, eh.x); sv.y = fmaf(sv.y, es.y, eh.y);
+                  sv.z = fmaf(sv.z, es.z, eh.z); sv.w = fmaf(sv.w, es.w, eh.w);
+                }
+              }
+              o.x = sv.x > 0.f ? o.x : 0.f; o.y = sv.y > 0.f ? o.y : 0.f;
+              o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(out + orow * Cout + cc + j) = o;
+          }
+          }
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&ctl->acc_empty[h]);
+    }
+  } else if (warp == 8) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      uint32_t idesc[4];
+      for (int n = 1; n <= 3; ++n) idesc[n] = make_idesc_tf32(FW_TM, n * Cout);
+      const uint32_t W_LBO = (uint32_t)(3 * Cout) * 16, W_PART = FW_KCH * W_LBO;
+      const uint32_t w_base = smem_u32(w_smem), a_base = smem_u32(a_smem);
+      int it = 0, li = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+        const int fc = item % p.f_chunks;
+        const int fo0 = fc * R, h = li & 1;
+        const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
+        mbar_wait(&ctl->acc_empty[h], ((li >> 1) & 1) ^ 1);          // the epilogue drained + re-zeroed this half
+        tc_fence_after();
+        for (int f = f_lo; f <= f_hi; ++f) {
+          const int rlo = max(f - 1, fo0), rhi = min(f + 1, fo0 + R - 1);
+          const int blk0 = rlo - (f - 1), nblk = rhi - rlo + 1;
+          const uint32_t d = tmem_base + (uint32_t)(h * 256 + (rlo - fo0) * Cout);
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int slot = it % FW_NA;
+            mbar_wait(&ctl->a_full[slot], (it / FW_NA) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = a_base + slot * FW_A_STAGE, a_lo = a_hi + FW_A_PART;
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+              const uint32_t w_hi = w_base + (uint32_t)((dt * p.nkb + kb) * 2) * W_PART + (uint32_t)(blk0 * Cout) * 16;
+              const uint32_t w_lo = w_hi + W_PART;
+#pragma unroll
+              for (int ks = 0; ks < FW_KB / 8; ++ks) {
+                const uint32_t ao = (uint32_t)dt * 16 + (uint32_t)(ks * 2) * FW_A_LBO, wo = (uint32_t)(ks * 2) * W_LBO;
+                const uint64_t dah = make_desc(a_hi + ao, FW_A_LBO, 128), dal = make_desc(a_lo + ao, FW_A_LBO, 128);
+                const uint64_t dwh = make_desc(w_hi + wo, W_LBO, 128), dwl = make_desc(w_lo + wo, W_LBO, 128);
+                mma_tf32(d, dah, dwh, idesc[nblk], 1u);
+                if (!p.single) {
+                  mma_tf32(d, dal, dwh, idesc[nblk], 1u);
+                  mma_tf32(d, dah, dwl, idesc[nblk], 1u);
+                }
+              }
+            }
+            mma_commit(&ctl->a_empty[slot]);
+          }
+          // strip f was the last contribution to output row f-1 (and, at the bottom of the map, to row f)
+          if (f - 1 >= fo0) mma_commit(&ctl->acc_full[h][f - 1 - fo0]);
+          if (f == f_hi)
+            for (int r = max(f, fo0); r <= fo0 + R - 1; ++r) mma_commit(&ctl->acc_full[h][r - fo0]);
+        }
+      }
+    }
+  } else {
+    // ============================== TMA loader ==============================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
+        const int fo0 = fc * R, t0 = tt * FW_TM;
+        const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
+        for (int f = f_lo; f <= f_hi; ++f)
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int rs = it % FW_NRAW;
+            mbar_wait(&ctl->raw_empty[rs], ((it / FW_NRAW) & 1) ^ 1);
+            mbar_expect_tx(&ctl->raw_full[rs], FW_RAW_STAGE);
+            tma_load_2d(r_smem + rs * FW_RAW_STAGE, &tm_in, kb * FW_KB, (b * p.F + f) * p.T + t0 - 1, &ctl->raw_full[rs]);
+          }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// *handled = 1: `out` holds the finished map (bias / ReLU-mask epilogue applied); fused column sums are NOT
+// produced -- the caller (pbsed_tapgemm) runs them as separate passes over `out`.
+int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale, const float* shift,
+                        const int* seq_len, const float* W, const float* bias, float* out, const float* ep_src,
+                        const float* ep_scale, const float* ep_shift, void* workspace, long long ws_bytes,
+                        cudaStream_t st, int* handled) {
+  *handled = 0;
+  static const int enabled = getenv("PBSED_FW") ? atoi(getenv("PBSED_FW")) : 1;
+  if (!enabled || (d->precision != 1 && d->precision != 3) || !workspace) return 0;
+  if (d->ntaps != 9 || d->F_in != d->F_out || d->per_f) return 0;
+  if ((d->Cin != 16 && d->Cin != 32) || (d->Cout != 16 && d->Cout != 32)) return 0;
+  if ((d->in_stride > 0 && d->in_stride != d->Cin) || (d->out_stride > 0 && d->out_stride != d->Cout)) return 0;
+  int tapidx[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) tapidx[i][j] = -1;
+  for (int i = 0; i < 9; ++i) {
+    if (d->df[i] < -1 || d->df[i] > 1 || d->dt[i] < -1 || d->dt[i] > 1) return 0;
+    tapidx[d->df[i] + 1][d->dt[i] + 1] = i;
+  }
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) if (tapidx[i][j] < 0) return 0;
+  FwParams p = {};
+  p.B = d->B; p.F = d->F_in; p.T = d->T; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.relu = d->relu; p.single = d->precision == 3;
+  p.nkb = d->Cin / FW_KB;
+  p.R = 256 / d->Cout;
+  if (p.F % p.R) return 0;
+  p.t_tiles = cdiv(p.T, FW_TM);
+  p.f_chunks = p.F / p.R;
+  const long long items = (long long)p.B * p.t_tiles * p.f_chunks;
+  const long long rows = (long long)p.B * p.F * p.T;
+  if (items > (1 << 30) || rows >= (1LL << 31) - 256) return 0;
+  p.items = (int)items;
+  p.w_bytes = 3u * p.nkb * 2u * FW_KCH * (3u * p.Cout) * 16u;
+  if ((long long)p.w_bytes > ws_bytes) return 0;
+  if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
+        (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift) & 15) != 0)
+    return 0;
+  CUtensorMap tm_in;
+  if (!make_tmap_2d(&tm_in, in, p.Cin, rows, p.Cin, FW_KB, FW_ROWS)) return 0;
+  float* img = reinterpret_cast<float*>(workspace);
+  fwprep_kernel<<<cdiv(p.w_bytes / 8, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,
+      tapidx[0][0], tapidx[0][1], tapidx[0][2], tapidx[1][0], tapidx[1][1], tapidx[1][2],
+      tapidx[2][0], tapidx[2][1], tapidx[2][2], img, p.single);
+  int rc = pbsed_after_launch();
+  if (rc) return rc;
+  const size_t smem = (size_t)p.w_bytes + FW_NA * FW_A_STAGE + FW_NRAW * FW_RAW_STAGE + sizeof(FwCtl) + 128;
+  cudaError_t e = cudaFuncSetAttribute(tapgemm_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int grid = p.items < n_sm ? p.items : n_sm;
+  pbsed_note_kernel("tapgemm_fw_kernel");
+  tapgemm_fw_kernel<<<grid, FW_THREADS, smem, st>>>(p, tm_in, scale, shift, seq_len,
+                                                   d->no_input_mask ? nullptr : seq_len, img, bias, out, ep_src,
+                                                   ep_scale, ep_shift);
+  *handled = 1;
+  return pbsed_after_launch();
+}

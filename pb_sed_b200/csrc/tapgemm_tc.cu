@@ -25,6 +25,7 @@
 // Operand layouts are the canonical UMMA K-major SWIZZLE_NONE ("interleave") form:
 //   byte(row r, 16-byte k-chunk c) = c*LBO + (r/8)*SBO + (r%8)*16   with SBO = 128  => row pitch 16.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cstdlib>
 
 namespace {
@@ -50,88 +51,6 @@ struct TcParams {
   int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
   int single;            // 1: one TF32 pass (precision 3), no lo parts
 };
-
-// round-to-nearest TF32 (single-pass mode; the split mode truncates because hi + lo is exact either way)
-__device__ __forceinline__ float tf32_rn(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u);
-}
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout:
-// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2)
-// [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------ weight image
 // image[slice][tap][kb] = { part hi | part lo } x [k-chunk (4)][n (N)][4 floats]
@@ -804,6 +723,262 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
   }
 }
 
+
+// =====================================================================================
+// wgrad_tma_kernel: the same tensor-core weight gradient, with the global loads taken OFF the producers'
+// critical path.  A loader thread streams RAW fp32 tiles -- dout [32 frames x Ms channels] and the layer input
+// [34 frames x Nc channels, one halo frame each side] -- with 2-D tensor-map TMA copies
+// (cp.async.bulk.tensor -> UTMALDG) into a ring of WG_RAW_MAX-deep raw stages, several stages ahead of the
+// tensor pipe.  The 8 producer warps became CONVERTERS: they read a landed raw tile from shared memory, apply
+// sequence mask / norm / ReLU, transpose 4x4 in registers and write the K-major hi/lo operand images the MMAs
+// consume (same images, same MMA issue as wgrad_tc_kernel).  Measured motive: wgrad_tc_kernel's producers
+// stalled on their own LDGs (ncu: long-scoreboard on the first use, 68 % of issue slots idle); the 1-tap
+// GRU / output_net gradients, whose stages carry only 12 MMAs, were pure load latency.
+// Rows a box fetches beyond its (b, f) row group are neighbours' frames or hardware zero fill: the converters
+// select by frame index, so they never reach an operand.
+constexpr int WG_RAW_MAX = 6;
+constexpr int WG_RAW_AROWS = WG_KR + 2;
+
+struct __align__(16) WgTmaCtl {
+  uint64_t full[WG_STAGES], empty[WG_STAGES], raw_full[WG_RAW_MAX], raw_empty[WG_RAW_MAX], acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WG_PROD + 64)
+wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_a,
+                 int raw_stages, const float* __restrict__ scale, const float* __restrict__ shift,
+                 const int* __restrict__ seq_len, const float* __restrict__ dout, float* __restrict__ dW,
+                 float* __restrict__ dbias) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int zq = p.Ms / 4, aq = p.Nc / 4;           // channel quads per operand
+  const uint32_t Z_LBO = 128 * 16, A_LBO = (uint32_t)p.Nc * 16;
+  const uint32_t Z_PART = WG_ZCH * Z_LBO, A_PART = WG_ACH * A_LBO;
+  const uint32_t STAGE = 2 * Z_PART + 2 * A_PART;
+  const uint32_t RAW_Z = WG_KR * (uint32_t)p.Ms * 4, RAW_A = WG_RAW_AROWS * (uint32_t)p.Nc * 4;
+  const uint32_t RAW = RAW_Z + RAW_A;
+  uint8_t* raw_base = smem_raw + WG_STAGES * STAGE;
+  WgTmaCtl* ctl = reinterpret_cast<WgTmaCtl*>(raw_base + (uint32_t)raw_stages * RAW);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int c_slice = blockIdx.z % p.c_slices, m_slice = blockIdx.z / p.c_slices;
+  const int m0 = m_slice * p.Ms, c0 = c_slice * p.Nc;
+  const int df = p.g_df[g], ntap = p.g_n[g];
+  const int t_blocks = (p.T + WG_TB - 1) / WG_TB;
+  const int total_units = p.B * p.F_out * t_blocks;
+  const bool do_bias = dbias != nullptr && g == 0 && c_slice == 0;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ntap * p.Nc) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&ctl->full[i], WG_PROD); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < raw_stages; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], WG_PROD); }
+    mbar_init(&ctl->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_PROD / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (p.Ms < 128) {      // operand rows m >= Ms are read by the M = 128 MMA but never produced: zero once
+    for (int s = 0; s < WG_STAGES; ++s)
+      for (int part = 0; part < 2; ++part)
+        for (int ch = 0; ch < WG_ZCH; ++ch) {
+          float4* base = reinterpret_cast<float4*>(smem_raw + s * STAGE + part * Z_PART + ch * Z_LBO);
+          for (int i = p.Ms + tid; i < 128; i += WG_PROD + 64) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < WG_PROD / 32) {
+    // ============================== converters ==============================
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int zqi = tid % zq, aqi = tid % aq;
+    const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+      const int tb = u % t_blocks, gq = u / t_blocks;
+      const int fo = gq % p.F_out, b = gq / p.F_out;
+      const int f_src = fo + df;
+      const bool f_ok = f_src >= 0 && f_src < p.F_in;
+      if (!f_ok && !do_bias) continue;
+      const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+      const int len_out = p.mask_out ? len_b : p.T;
+      const int t_end = min(p.T, (tb + 1) * WG_TB);
+      if (!f_ok) {                                 // bias-only visit of a border row group: plain loads
+        const float* zsrc = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR)
+          for (int j = zj0; j < WG_ZCH; j += zjs)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = t0 + j + 8 * i;
+              if (t < len_out) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+              }
+            }
+        continue;
+      }
+      if (scale) {
+        const int aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
+        sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
+        sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+      }
+      for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
+        const int rs = it % raw_stages, slot = it % WG_STAGES;
+        const float* rz = reinterpret_cast<const float*>(raw_base + (uint32_t)rs * RAW);
+        const float* ra = reinterpret_cast<const float*>(raw_base + (uint32_t)rs * RAW + RAW_Z);
+        uint8_t* z_hi = smem_raw + slot * STAGE;
+        uint8_t* z_lo = z_hi + Z_PART;
+        uint8_t* a_hi = z_lo + Z_PART;
+        uint8_t* a_lo = a_hi + A_PART;
+        mbar_wait(&ctl->raw_full[rs], (it / raw_stages) & 1);          // the raw tile has landed
+        mbar_wait(&ctl->empty[slot], ((it / WG_STAGES) & 1) ^ 1);      // the MMAs released the operand stage
+        for (int j = zj0; j < WG_ZCH; j += zjs) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = j + 8 * i;
+            v[i] = (t0 + r < len_out) ? *reinterpret_cast<const float4*>(rz + r * p.Ms + zqi * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
+          split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+          split_store(z_hi, z_lo, o + 1 * zq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+          split_store(z_hi, z_lo, o + 2 * zq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+          split_store(z_hi, z_lo, o + 3 * zq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
+          if (do_bias) {
+            bsum.x += (v[0].x + v[1].x) + (v[2].x + v[3].x); bsum.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
+            bsum.z += (v[0].z + v[1].z) + (v[2].z + v[3].z); bsum.w += (v[0].w + v[1].w) + (v[2].w + v[3].w);
+          }
+        }
+        for (int jj = aj0; jj < WG_ACH; jj += ajs) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = jj + 8 * i, t = t0 + r - 1;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < len_b) {
+              x = *reinterpret_cast<const float4*>(ra + r * p.Nc + aqi * 4);
+              if (scale) {
+                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+              }
+              if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+            v[i] = x;
+          }
+          const uint32_t o = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
+          split_store(a_hi, a_lo, o + 0 * aq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
+          split_store(a_hi, a_lo, o + 1 * aq * 16, v[0].y, v[1].y, v[2].y, v[3].y, p.single);
+          split_store(a_hi, a_lo, o + 2 * aq * 16, v[0].z, v[1].z, v[2].z, v[3].z, p.single);
+          split_store(a_hi, a_lo, o + 3 * aq * 16, v[0].w, v[1].w, v[2].w, v[3].w, p.single);
+        }
+        mbar_arrive(&ctl->raw_empty[rs]);            // raw tile consumed: the loader may refill it
+        fence_async_smem();
+        mbar_arrive(&ctl->full[slot]);
+      }
+    }
+    if (do_bias) {
+      float* db = dbias + m0 + zqi * 4;
+      if (bsum.x != 0.f) atomicAdd(db + 0, bsum.x);
+      if (bsum.y != 0.f) atomicAdd(db + 1, bsum.y);
+      if (bsum.z != 0.f) atomicAdd(db + 2, bsum.z);
+      if (bsum.w != 0.f) atomicAdd(db + 3, bsum.w);
+    }
+    // ============================== epilogue ==============================
+    mbar_wait(&ctl->acc_full, 0);
+    tc_fence_after();
+    const int lw = warp & 3, half = warp >> 2;              // TMEM lane quarter / column half
+    const int m = lw * 32 + lane;                            // operand row -> channel (quad-major)
+    const int n = m0 + 4 * (m % zq) + m / zq;
+    if (it > 0) {                                            // no MMA issued -> TMEM is uninitialised
+      for (int j = 0; j < ntap; ++j) {
+        float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
+        for (int cc = half * 16; cc < p.Nc; cc += 32) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
+          if (m < p.Ms) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int ci = cc + k;
+              const int c = c0 + 4 * (ci % aq) + ci / aq;
+              if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == WG_PROD / 32) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TILE_M, p.Nc);
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out;
+        const int f_src = fo + df;
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR) {
+          const int slot = it % WG_STAGES;
+          mbar_wait(&ctl->full[slot], (it / WG_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t z_hi = smem_u32(smem_raw + slot * STAGE), z_lo = z_hi + Z_PART;
+          const uint32_t a_hi = z_lo + Z_PART, a_lo = a_hi + A_PART;
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
+            const int dt = p.g_dt[g][j];
+#pragma unroll
+            for (int ks = 0; ks < WG_KR / 8; ++ks) {
+              const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
+              const uint64_t dzh = make_desc(z_hi + zo, Z_LBO, 128), dzl = make_desc(z_lo + zo, Z_LBO, 128);
+              const uint64_t dah = make_desc(a_hi + ao, A_LBO, 128), dal = make_desc(a_lo + ao, A_LBO, 128);
+              mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+              if (!p.single) {
+                mma_tf32(d, dzl, dah, idesc, 1u);
+                mma_tf32(d, dzh, dal, idesc, 1u);
+              }
+            }
+          }
+          mma_commit(&ctl->empty[slot]);
+          ++it;
+        }
+      }
+      mma_commit(&ctl->acc_full);
+    }
+  } else {
+    // ============================== TMA loader ==============================
+    if (lane == 0) {
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out, b = gq / p.F_out;
+        const int f_src = fo + df;
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
+        const int zrow = (b * p.F_out + fo) * p.T, arow = (b * p.F_in + f_src) * p.T;
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
+          const int rs = it % raw_stages;
+          mbar_wait(&ctl->raw_empty[rs], ((it / raw_stages) & 1) ^ 1);
+          uint8_t* dst = raw_base + (uint32_t)rs * RAW;
+          mbar_expect_tx(&ctl->raw_full[rs], RAW);
+          tma_load_2d(dst, &tm_z, m0, zrow + t0, &ctl->raw_full[rs]);
+          tma_load_2d(dst + RAW_Z, &tm_a, c0, arow + t0 - 1, &ctl->raw_full[rs]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == WG_PROD / 32) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace
 
 // per-row-tile "first" flag: the first MMA into EACH accumulator must overwrite.  The loop above
@@ -911,6 +1086,8 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   return pbsed_after_launch();
 }
 
+
+
 int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                               const float* shift, const int* seq_len, const float* dout,
                               int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
@@ -943,6 +1120,33 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   }
   const int roles = p.ngroups * p.m_slices * p.c_slices;
   const int units = p.B * p.F_out * cdiv(p.T, WG_TB);
+  const size_t stage = 2 * (size_t)WG_ZCH * 128 * 16 + 2 * (size_t)WG_ACH * p.Nc * 16;
+  // ---- TMA-fed variant (default): raw tiles by tensor-map loads, as many raw stages as shared memory holds
+  static const int use_tma = getenv("PBSED_WG_TMA") ? atoi(getenv("PBSED_WG_TMA")) : 1;
+  const long long rows_z = (long long)p.B * p.F_out * p.T, rows_a = (long long)p.B * p.F_in * p.T;
+  if (use_tma && rows_z < (1LL << 31) && rows_a < (1LL << 31)) {
+    const size_t raw = (size_t)WG_KR * p.Ms * 4 + (size_t)WG_RAW_AROWS * p.Nc * 4;
+    const size_t budget = 227 * 1024 - WG_STAGES * stage - sizeof(WgTmaCtl) - 256;
+    int raw_stages = (int)(budget / raw);
+    if (raw_stages > WG_RAW_MAX) raw_stages = WG_RAW_MAX;
+    CUtensorMap tm_z, tm_a;
+    if (raw_stages >= 2 &&
+        make_tmap_2d(&tm_z, dout, p.Cout, rows_z, p.out_stride, p.Ms, WG_KR) &&
+        make_tmap_2d(&tm_a, in, p.Cin, rows_a, p.in_stride, p.Nc, WG_RAW_AROWS)) {
+      int rs = 148 / roles;                            // one CTA per SM: a single wave, deep prefetch instead of co-residency
+      if (rs > units) rs = units;
+      if (rs < 1) rs = 1;
+      p.row_splits = rs;
+      const size_t smem = WG_STAGES * stage + (size_t)raw_stages * raw + sizeof(WgTmaCtl) + 128;
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      dim3 grid(rs, p.ngroups, p.m_slices * p.c_slices);
+      pbsed_note_kernel("wgrad_tma_kernel");
+      wgrad_tma_kernel<<<grid, WG_PROD + 64, smem, st>>>(p, tm_z, tm_a, raw_stages, scale, shift, seq_len, dout, dW, dbias);
+      *handled = 1;
+      return pbsed_after_launch();
+    }
+  }
   int rs = (2 * 148) / roles;                       // <= 2 CTAs per SM's worth, never a ragged extra wave
   if (rs >= 8 * 2 && units / rs < 4) rs = 148 / roles;
   // 128-wide input slices need 147 KB of shared memory: ONE CTA per SM, so 2 x 148 CTAs would run as two
@@ -952,7 +1156,6 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   if (rs > units) rs = units;
   if (rs < 1) rs = 1;
   p.row_splits = rs;
-  const size_t stage = 2 * (size_t)WG_ZCH * 128 * 16 + 2 * (size_t)WG_ACH * p.Nc * 16;
   const size_t smem = WG_STAGES * stage + sizeof(WgCtl) + 128;
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
