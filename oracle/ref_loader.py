@@ -28,7 +28,12 @@ import numpy as np
 
 from . import pt_port
 
-REFERENCE_ROOT = os.environ.get('PB_SED_REFERENCE', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the UNMODIFIED pip install of the reference under
+# baseline/_ref (git-ignored, travels with the snapshot; `pip install --no-deps --target baseline/_ref`)
+REFERENCE_ROOT = os.environ.get('PB_SED_REFERENCE') or next(
+    (r for r in ('/root/reference', os.path.join(os.path.dirname(_HERE), 'baseline', '_ref'))
+     if os.path.isfile(os.path.join(r, 'pb_sed', 'models', 'weak_label', 'crnn.py'))), '/root/reference')
 
 
 def reference_available():
@@ -64,14 +69,20 @@ def segment_axis(x, length, shift, axis=-1, end='cut'):
 _loaded = {}
 
 
-def load():
-    """returns (weak_label_crnn_module, strong_label_crnn_module)."""
-    if 'weak' in _loaded:
-        return _loaded['weak'], _loaded['strong']
+def load(modules=None):
+    """returns (weak_label_crnn_module, strong_label_crnn_module): the reference's model sources executed
+    unmodified.  ``modules``: the namespace the ``padertorch.contrib.je.modules.*`` imports resolve to --
+    default the oracle restatements (``pt_port``); pass ``pb_sed_b200.modules`` to run the REAL pb_sed CRNN
+    classes over the sm_100a modules (the drop-in check of tests/test_gpu_reference_dropin.py)."""
+    key = 'oracle' if modules is None else modules.__name__
+    if ('weak', key) in _loaded:
+        return _loaded[('weak', key)], _loaded[('strong', key)]
     assert reference_available(), REFERENCE_ROOT
     if not hasattr(np, 'int'):       # pb_sed uses the removed alias (weak_label/crnn.py:252)
         np.int = int
-    P = pt_port
+    P = pt_port if modules is None else modules
+    if not hasattr(P, 'Model'):
+        P = types.SimpleNamespace(**{k: getattr(P, k) for k in dir(P) if not k.startswith('__')}, Model=pt_port.Model)
     _stub('padertorch', Model=P.Model)
     _stub('padertorch.ops')
     _stub('padertorch.ops.sequence')
@@ -98,7 +109,7 @@ def load():
     sys.modules['pb_sed.models'].base = base
     weak = _exec('pb_sed.models.weak_label.crnn', 'pb_sed/models/weak_label/crnn.py')
     strong = _exec('pb_sed.models.strong_label.crnn', 'pb_sed/models/strong_label/crnn.py')
-    _loaded.update(weak=weak, strong=strong)
+    _loaded[('weak', key)], _loaded[('strong', key)] = weak, strong
     return weak, strong
 
 

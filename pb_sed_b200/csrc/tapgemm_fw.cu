@@ -7,8 +7,10 @@
 // every input row for three output rows, and runs 16 k short-lived CTAs whose load -> convert -> MMA -> epilogue
 // chain never overlaps itself (measured r02: 277 us for 262 MB of algorithmic traffic, DRAM at 15 %, tensor pipe
 // at 14 %).  Here one PERSISTENT CTA per SM walks the frequency axis of a (clip, 128-frame) tile:
-//   * every input strip (row f, 130 frames incl. halo, 16 channels) is fetched ONCE -- by tensor-map TMA
-//     (cp.async.bulk.tensor) into an 8-deep raw ring -- converted once (norm + ReLU + mask + hi/lo split) and
+//   * every input strip (row f, 130 frames incl. halo, all Cin channels: one CONTIGUOUS block of the (B,F,T,C) map)
+//     is fetched ONCE -- by a 1-D bulk copy (cp.async.bulk -> UBLKCP) into a 4/8-deep raw ring; a tensor-map
+//     box with 64-byte rows measured 3x slower, the TMA unit pays per row -- converted once (norm + ReLU + mask +
+//     hi/lo split) and
 //     feeds the THREE output rows f-1, f, f+1 with one MMA per time tap: the weights of df = +1 / 0 / -1 are
 //     stacked along N (N = 3 x Cout = 48 / 96), the three rows' accumulators are adjacent TMEM columns;
 //   * a whole layer's weight image (<= 72 KB incl. hi/lo) stays resident in shared memory;
@@ -28,12 +30,11 @@ constexpr int FW_TM = 128;                 // frames per tile (= MMA M)
 constexpr int FW_ROWS = FW_TM + 2;         // strip rows incl. one halo frame each side
 constexpr int FW_KB = 16, FW_KCH = 4;      // channels / 16-byte chunks per stage
 constexpr int FW_NA = 3;                   // converted operand stages
-constexpr int FW_NRAW = 8;                 // raw (TMA) stages
+constexpr int FW_NRAW = 8;                 // raw (bulk-copy) stages at Cin = 16; 4 at Cin = 32 (same bytes)
 constexpr int FW_MAXR = 16;                // output rows per TMEM half (Cout = 16)
 constexpr uint32_t FW_A_LBO = FW_ROWS * 16;
 constexpr uint32_t FW_A_PART = FW_KCH * FW_A_LBO;      // 8320 B: one hi (or lo) strip stage
 constexpr uint32_t FW_A_STAGE = 2 * FW_A_PART;
-constexpr uint32_t FW_RAW_STAGE = FW_ROWS * FW_KB * 4; // 8320 B
 constexpr int FW_THREADS = 320;            // 4 converter warps, 4 epilogue warps, MMA warp, TMA warp
 
 struct FwParams {
@@ -42,6 +43,8 @@ struct FwParams {
   int nkb, R;                 // channel blocks of 16; output rows per item (= 256 / Cout)
   int t_tiles, f_chunks, items;
   unsigned w_bytes;
+  int nraw;                   // raw ring depth
+  unsigned raw_stage;         // bytes of one raw strip: 130 frames x Cin floats
 };
 
 struct __align__(16) FwCtl {
@@ -79,7 +82,7 @@ fwprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_s
 }
 
 __global__ void __launch_bounds__(FW_THREADS, 1)
-tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ scale,
+tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const int* __restrict__ load_seq_len, const float* __restrict__ wimg,
                   const float* __restrict__ bias, float* __restrict__ out, const float* __restrict__ ep_src,
@@ -88,12 +91,12 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
   uint8_t* w_smem = smem_raw;
   uint8_t* a_smem = w_smem + p.w_bytes;
   uint8_t* r_smem = a_smem + FW_NA * FW_A_STAGE;
-  FwCtl* ctl = reinterpret_cast<FwCtl*>(r_smem + FW_NRAW * FW_RAW_STAGE);
+  FwCtl* ctl = reinterpret_cast<FwCtl*>(r_smem + p.nraw * p.raw_stage);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Cout = p.Cout, R = p.R;
 
   if (tid == 0) {
-    for (int i = 0; i < FW_NRAW; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], 128); }
+    for (int i = 0; i < p.nraw; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], 128); }
     for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
     for (int h = 0; h < 2; ++h) {
       for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], 1);
@@ -120,24 +123,25 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
   if (warp < 4) {
     // ============================== converters ==============================
     const int c = tid & 3, r0 = tid >> 2;
-    int it = 0;
+    int it = 0, sit = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
       const int fo0 = fc * R, t0 = tt * FW_TM;
       const int len_in = load_seq_len ? min(__ldg(load_seq_len + b), p.T) : p.T;
       const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
-      for (int f = f_lo; f <= f_hi; ++f)
+      for (int f = f_lo; f <= f_hi; ++f, ++sit) {
+        const int rs = sit % p.nraw;
+        const float* raw = reinterpret_cast<const float*>(r_smem + rs * p.raw_stage);
+        mbar_wait(&ctl->raw_full[rs], (sit / p.nraw) & 1);             // the raw strip has landed
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (scale) {
             sc = __ldg(reinterpret_cast<const float4*>(scale + kb * FW_KB + c * 4));
             sh = __ldg(reinterpret_cast<const float4*>(shift + kb * FW_KB + c * 4));
           }
-          const int rs = it % FW_NRAW, slot = it % FW_NA;
-          const float* raw = reinterpret_cast<const float*>(r_smem + rs * FW_RAW_STAGE);
+          const int slot = it % FW_NA;
           uint8_t* hi_base = a_smem + slot * FW_A_STAGE;
           uint8_t* lo_base = hi_base + FW_A_PART;
-          mbar_wait(&ctl->raw_full[rs], (it / FW_NRAW) & 1);
           mbar_wait(&ctl->a_empty[slot], ((it / FW_NA) & 1) ^ 1);
 #pragma unroll
           for (int u = 0; u < (FW_ROWS + 31) / 32; ++u) {
@@ -145,7 +149,7 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
             if (r >= FW_ROWS) break;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t >= 0 && t < len_in) {
-              x = *reinterpret_cast<const float4*>(raw + r * FW_KB + c * 4);
+              x = *reinterpret_cast<const float4*>(raw + r * p.Cin + kb * FW_KB + c * 4);
               if (scale) {
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
@@ -165,10 +169,11 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
               *reinterpret_cast<float4*>(lo_base + o) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
             }
           }
-          mbar_arrive(&ctl->raw_empty[rs]);
           fence_async_smem();
           mbar_arrive(&ctl->a_full[slot]);
         }
+        mbar_arrive(&ctl->raw_empty[rs]);              // every channel block of the strip is converted
+      }
     }
   } else if (warp < 8) {
     // ============================== epilogue ==============================
@@ -183,9 +188,17 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
       const bool in_map = t < p.T;
       for (int r = 0; r < R; ++r) {
         const long long orow = ((long long)b * p.F + fo0 + r) * p.T + t;
+        float4 src[8];                                 // this frame's row of the ReLU-mask source: in flight during the wait
+        if (ep_src && in_map && t < len_b) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (4 * q < Cout) src[q] = __ldg(reinterpret_cast<const float4*>(ep_src + orow * Cout + 4 * q));
+        }
         mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
         tc_fence_after();
-        for (int cc = 0; cc < Cout; cc += 16) {
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 16) {
+          if (cc >= Cout) break;
           const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(h * 256 + r * Cout + cc);
           float v[16];
           tmem_ld16(ta, v);
@@ -201,7 +214,7 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
             if (ep_src) {                              // ReLU / sequence mask of a data-gradient pass
               float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
               if (t < len_b) {
-                sv = __ldg(reinterpret_cast<const float4*>(ep_src + orow * Cout + cc + j));
+                sv = src[(cc + j) >> 2];
                 if (ep_scale) {
                   const float4 es = __ldg(reinterpret_cast<const float4*>(ep_scale + cc + j));
                   const float4 eh = __ldg(reinterpret_cast<const float4*>(ep_shift + cc + j));
@@ -270,20 +283,24 @@ tapgemm_fw_kernel(FwParams p, const __grid_constant__ CUtensorMap tm_in, const f
       }
     }
   } else {
-    // ============================== TMA loader ==============================
+    // ============================== strip loader ==============================
+    // one 1-D bulk copy per strip: frames [max(t0-1, 0), min(t0+128, T-1)] of row group (b, f) are contiguous;
+    // the copy never leaves the row group, the converters never read the rows it left untouched
     if (lane == 0) {
-      int it = 0;
+      int sit = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
         const int fo0 = fc * R, t0 = tt * FW_TM;
         const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
-        for (int f = f_lo; f <= f_hi; ++f)
-          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-            const int rs = it % FW_NRAW;
-            mbar_wait(&ctl->raw_empty[rs], ((it / FW_NRAW) & 1) ^ 1);
-            mbar_expect_tx(&ctl->raw_full[rs], FW_RAW_STAGE);
-            tma_load_2d(r_smem + rs * FW_RAW_STAGE, &tm_in, kb * FW_KB, (b * p.F + f) * p.T + t0 - 1, &ctl->raw_full[rs]);
-          }
+        const int ta = max(t0 - 1, 0), tb = min(t0 + FW_TM, p.T - 1);
+        const uint32_t bytes = (uint32_t)(tb - ta + 1) * p.Cin * 4;
+        for (int f = f_lo; f <= f_hi; ++f, ++sit) {
+          const int rs = sit % p.nraw;
+          mbar_wait(&ctl->raw_empty[rs], ((sit / p.nraw) & 1) ^ 1);
+          mbar_expect_tx(&ctl->raw_full[rs], bytes);
+          bulk_g2s(r_smem + rs * p.raw_stage + (uint32_t)(ta - (t0 - 1)) * p.Cin * 4,
+                   in + (((long long)b * p.F + f) * p.T + ta) * p.Cin, bytes, &ctl->raw_full[rs]);
+        }
       }
     }
   }
@@ -333,15 +350,15 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
         (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift) & 15) != 0)
     return 0;
-  CUtensorMap tm_in;
-  if (!make_tmap_2d(&tm_in, in, p.Cin, rows, p.Cin, FW_KB, FW_ROWS)) return 0;
+  p.raw_stage = (unsigned)FW_ROWS * p.Cin * 4;
+  p.nraw = FW_NRAW * FW_KB / p.Cin;
   float* img = reinterpret_cast<float*>(workspace);
   fwprep_kernel<<<cdiv(p.w_bytes / 8, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,
       tapidx[0][0], tapidx[0][1], tapidx[0][2], tapidx[1][0], tapidx[1][1], tapidx[1][2],
       tapidx[2][0], tapidx[2][1], tapidx[2][2], img, p.single);
   int rc = pbsed_after_launch();
   if (rc) return rc;
-  const size_t smem = (size_t)p.w_bytes + FW_NA * FW_A_STAGE + FW_NRAW * FW_RAW_STAGE + sizeof(FwCtl) + 128;
+  const size_t smem = (size_t)p.w_bytes + FW_NA * FW_A_STAGE + (size_t)p.nraw * p.raw_stage + sizeof(FwCtl) + 128;
   cudaError_t e = cudaFuncSetAttribute(tapgemm_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   static int n_sm = 0;
@@ -353,7 +370,7 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   }
   const int grid = p.items < n_sm ? p.items : n_sm;
   pbsed_note_kernel("tapgemm_fw_kernel");
-  tapgemm_fw_kernel<<<grid, FW_THREADS, smem, st>>>(p, tm_in, scale, shift, seq_len,
+  tapgemm_fw_kernel<<<grid, FW_THREADS, smem, st>>>(p, in, scale, shift, seq_len,
                                                    d->no_input_mask ? nullptr : seq_len, img, bias, out, ep_src,
                                                    ep_scale, ep_shift);
   *handled = 1;
