@@ -218,7 +218,8 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
 
 int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale, const float* shift,
                         const int* seq_len, const float* W, const float* bias, float* out, const float* ep_src,
-                        const float* ep_scale, const float* ep_shift, void* workspace, long long ws_bytes,
+                        const float* ep_scale, const float* ep_shift, double* out_stats, const float* ep_mean,
+                        const float* ep_rstd, double* ep_sums, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled);
 int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                            const float* shift, const int* seq_len, const float* W, const float* bias,
@@ -266,21 +267,19 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   const int* load_seq = d->no_input_mask ? nullptr : seq_len;
   int fw_done = 0;
   if (d->precision != 0) {
-    // narrow 3x3 layers: the frequency-walking persistent kernel (no fused column sums: separate passes below)
+    // narrow 3x3 layers: the frequency-walking persistent kernel
     rc = tapgemm_fw_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
-                             workspace, workspace_bytes, st, &fw_done);
-    if (rc) return rc;
-    if (!fw_done) {
+                             out_stats, ep_mean, ep_rstd, ep_sums, workspace, workspace_bytes, st, &fw_done);
+    if (fw_done || rc) return rc;
+    {
       int handled = 0;
       rc = tapgemm_tc_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
                                out_stats, ep_mean, ep_rstd, ep_sums, workspace, workspace_bytes, st, &handled);
       if (handled || rc) return rc;
     }
   }
-  if (!fw_done) {
-    rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
-    if (rc) return rc;
-  }
+  rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
+  if (rc) return rc;
   // kernels without fused reductions: run them as separate passes over the finished map
   if (out_stats) {
     rc = pbsed_channel_stats(out, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, out_stats, stream);

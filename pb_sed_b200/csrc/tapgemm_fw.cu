@@ -51,14 +51,17 @@ struct __align__(16) FwCtl {
   uint64_t raw_full[FW_NRAW], raw_empty[FW_NRAW], a_full[FW_NA], a_empty[FW_NA];
   uint64_t acc_full[2][FW_MAXR], acc_empty[2];
   uint32_t tmem_base;
+  float colacc[2][32];        // per-CTA column sums of the fused statistics
 };
+constexpr int FW_STAT_REP = 32;   // global accumulators are replicated: CTAs hash onto them, a fold kernel sums
 
 // weight image: [dt 3][kb][part hi|lo][k-chunk 4][n' = blk * Cout + n][4 floats], blk 0/1/2 <-> df = +1/0/-1,
 // i.e. the output rows f-1, f, f+1 a source strip f contributes to
 __global__ void __launch_bounds__(256)
 fwprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
               int Cin, int Cout, int t00, int t01, int t02, int t10, int t11, int t12, int t20, int t21, int t22,
-              float* __restrict__ img, int single) {
+              float* __restrict__ img, int single, double* __restrict__ rep, int rep_count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rep_count; i += gridDim.x * blockDim.x) rep[i] = 0.;
   const int tapidx[3][3] = {{t00, t01, t02}, {t10, t11, t12}, {t20, t21, t22}};   // [df+1][dt+1]
   const int nkb = Cin / FW_KB, N3 = 3 * Cout;
   const int total = 3 * nkb * FW_KCH * N3 * 4;
@@ -86,7 +89,9 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const int* __restrict__ load_seq_len, const float* __restrict__ wimg,
                   const float* __restrict__ bias, float* __restrict__ out, const float* __restrict__ ep_src,
-                  const float* __restrict__ ep_scale, const float* __restrict__ ep_shift) {
+                  const float* __restrict__ ep_scale, const float* __restrict__ ep_shift,
+                  double* __restrict__ out_stats, const float* __restrict__ ep_mean,
+                  const float* __restrict__ ep_rstd, double* __restrict__ ep_sums) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* w_smem = smem_raw;
   uint8_t* a_smem = w_smem + p.w_bytes;
@@ -105,6 +110,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) tmem_alloc(&ctl->tmem_base, 512);
+  if (tid < 64) ctl->colacc[tid >> 5][tid & 31] = 0.f;
   for (unsigned i = tid; i < p.w_bytes / 16; i += FW_THREADS)          // the layer's weights: resident for the whole kernel
     reinterpret_cast<float4*>(w_smem)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
   fence_async_smem();
@@ -179,6 +185,10 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     // ============================== epilogue ==============================
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
+    const bool want_sums = out_stats != nullptr || ep_sums != nullptr;
+    float s0[32], s1[32];                    // this frame-lane's column sums over every row it stores
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
     int li = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
       const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
@@ -226,6 +236,22 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
               o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
             }
             *reinterpret_cast<float4*>(out + orow * Cout + cc + j) = o;
+            if (want_sums && t < len_b) {
+              if (out_stats) {                         // next layer's batch statistics: sum, sum of squares
+                s0[cc + j] += o.x; s0[cc + j + 1] += o.y; s0[cc + j + 2] += o.z; s0[cc + j + 3] += o.w;
+                s1[cc + j] = fmaf(o.x, o.x, s1[cc + j]); s1[cc + j + 1] = fmaf(o.y, o.y, s1[cc + j + 1]);
+                s1[cc + j + 2] = fmaf(o.z, o.z, s1[cc + j + 2]); s1[cc + j + 3] = fmaf(o.w, o.w, s1[cc + j + 3]);
+              } else {                                 // batch-norm backward pass 1: sum g, sum g * xhat
+                const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + cc + j));
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + cc + j));
+                const float4 x = src[(cc + j) >> 2];
+                s0[cc + j] += o.x; s0[cc + j + 1] += o.y; s0[cc + j + 2] += o.z; s0[cc + j + 3] += o.w;
+                s1[cc + j] = fmaf(o.x, (x.x - mu.x) * rs.x, s1[cc + j]);
+                s1[cc + j + 1] = fmaf(o.y, (x.y - mu.y) * rs.y, s1[cc + j + 1]);
+                s1[cc + j + 2] = fmaf(o.z, (x.z - mu.z) * rs.z, s1[cc + j + 2]);
+                s1[cc + j + 3] = fmaf(o.w, (x.w - mu.w) * rs.w, s1[cc + j + 3]);
+              }
+            }
           }
           }
         }
@@ -233,6 +259,18 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&ctl->acc_empty[h]);
+    }
+    if (want_sums) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < Cout) { atomicAdd(&ctl->colacc[0][i], s0[i]); atomicAdd(&ctl->colacc[1][i], s1[i]); }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = tid - 128;
+      if (et < Cout) {
+        double* dst = (out_stats ? out_stats : ep_sums) + ((long long)(blockIdx.x % FW_STAT_REP) * Cout + et) * 2;
+        atomicAdd(dst, (double)ctl->colacc[0][et]);
+        atomicAdd(dst + 1, (double)ctl->colacc[1][et]);
+      }
     }
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
@@ -312,15 +350,26 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
   }
 }
 
+__global__ void fw_stat_fold_kernel(const double* __restrict__ rep, int n, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.;
+  for (int r = 0; r < FW_STAT_REP; ++r) s += rep[(long long)r * n + i];
+  dst[i] += s;
+}
+
 }  // namespace
 
-// *handled = 1: `out` holds the finished map (bias / ReLU-mask epilogue applied); fused column sums are NOT
-// produced -- the caller (pbsed_tapgemm) runs them as separate passes over `out`.
+// *handled = 1: `out` holds the finished map (bias / ReLU-mask epilogue applied) and the fused column sums
+// (out_stats / ep_sums, when asked for) have been added to the caller's accumulators.
 int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale, const float* shift,
                         const int* seq_len, const float* W, const float* bias, float* out, const float* ep_src,
-                        const float* ep_scale, const float* ep_shift, void* workspace, long long ws_bytes,
+                        const float* ep_scale, const float* ep_shift, double* out_stats, const float* ep_mean,
+                        const float* ep_rstd, double* ep_sums, void* workspace, long long ws_bytes,
                         cudaStream_t st, int* handled) {
   *handled = 0;
+  if (out_stats && ep_sums) return 0;
+  if (ep_sums && (!ep_src || !ep_mean || !ep_rstd)) return 0;
   static const int enabled = getenv("PBSED_FW") ? atoi(getenv("PBSED_FW")) : 1;
   if (!enabled || (d->precision != 1 && d->precision != 3) || !workspace) return 0;
   if (d->ntaps != 9 || d->F_in != d->F_out || d->per_f) return 0;
@@ -346,16 +395,19 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   if (items > (1 << 30) || rows >= (1LL << 31) - 256) return 0;
   p.items = (int)items;
   p.w_bytes = 3u * p.nkb * 2u * FW_KCH * (3u * p.Cout) * 16u;
-  if ((long long)p.w_bytes > ws_bytes) return 0;
+  const bool want_sums = out_stats || ep_sums;
+  const long long rep_bytes = (long long)FW_STAT_REP * p.Cout * 2 * sizeof(double);
+  if ((long long)p.w_bytes + 256 + (want_sums ? rep_bytes : 0) > ws_bytes) return 0;
+  double* rep = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + ((p.w_bytes + 255) / 256) * 256);
   if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
-        (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift) & 15) != 0)
+        (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift | (uintptr_t)ep_mean | (uintptr_t)ep_rstd) & 15) != 0)
     return 0;
   p.raw_stage = (unsigned)FW_ROWS * p.Cin * 4;
   p.nraw = FW_NRAW * FW_KB / p.Cin;
   float* img = reinterpret_cast<float*>(workspace);
   fwprep_kernel<<<cdiv(p.w_bytes / 8, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,
       tapidx[0][0], tapidx[0][1], tapidx[0][2], tapidx[1][0], tapidx[1][1], tapidx[1][2],
-      tapidx[2][0], tapidx[2][1], tapidx[2][2], img, p.single);
+      tapidx[2][0], tapidx[2][1], tapidx[2][2], img, p.single, rep, want_sums ? FW_STAT_REP * p.Cout * 2 : 0);
   int rc = pbsed_after_launch();
   if (rc) return rc;
   const size_t smem = (size_t)p.w_bytes + FW_NA * FW_A_STAGE + (size_t)p.nraw * p.raw_stage + sizeof(FwCtl) + 128;
@@ -372,7 +424,11 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   pbsed_note_kernel("tapgemm_fw_kernel");
   tapgemm_fw_kernel<<<grid, FW_THREADS, smem, st>>>(p, in, scale, shift, seq_len,
                                                    d->no_input_mask ? nullptr : seq_len, img, bias, out, ep_src,
-                                                   ep_scale, ep_shift);
+                                                   ep_scale, ep_shift, out_stats ? rep : nullptr, ep_mean, ep_rstd,
+                                                   ep_sums ? rep : nullptr);
   *handled = 1;
+  rc = pbsed_after_launch();
+  if (rc || !want_sums) return rc;
+  fw_stat_fold_kernel<<<cdiv(2 * p.Cout, 64), 64, 0, st>>>(rep, 2 * p.Cout, out_stats ? out_stats : ep_sums);
   return pbsed_after_launch();
 }

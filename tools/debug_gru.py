@@ -39,5 +39,7 @@ def run(B, In, bidir, T=120, H=256, ragged=True):
         if e > 2e-4:
             print('   param', k, f'{e:.2e}')
 
-for args in [(64, 266, True), (64, 256, True), (9, 266, True), (64, 266, False), (32, 266, True), (64, 266, True, 120, 256, False)]:
+import os
+cases = {'small': [(64, 266, False)], 'all': [(64, 266, True), (64, 256, True), (64, 266, False), (64, 272, False)]}[os.environ.get('GRU_CASES', 'all')]
+for args in cases:
     run(*args)
