@@ -52,6 +52,7 @@ struct __align__(16) FwCtl {
   uint64_t acc_full[2][FW_MAXR], acc_empty[2];
   uint32_t tmem_base;
   float colacc[2][32];        // per-CTA column sums of the fused statistics
+  float cvec[5][32];          // per-channel epilogue constants: bias, ep_scale, ep_shift, ep_mean, ep_rstd
 };
 constexpr int FW_STAT_REP = 32;   // global accumulators are replicated: CTAs hash onto them, a fold kernel sums
 
@@ -111,6 +112,11 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
   }
   if (warp == 8) tmem_alloc(&ctl->tmem_base, 512);
   if (tid < 64) ctl->colacc[tid >> 5][tid & 31] = 0.f;
+  if (tid >= 64 && tid < 224) {               // stage the per-channel epilogue vectors once (broadcast LDS later)
+    const int which = (tid - 64) >> 5, ch = tid & 31;
+    const float* srcv = which == 0 ? bias : which == 1 ? ep_scale : which == 2 ? ep_shift : which == 3 ? ep_mean : ep_rstd;
+    ctl->cvec[which][ch] = (srcv && ch < Cout) ? __ldg(srcv + ch) : (which == 1 || which == 4 ? 1.f : 0.f);
+  }
   for (unsigned i = tid; i < p.w_bytes / 16; i += FW_THREADS)          // the layer's weights: resident for the whole kernel
     reinterpret_cast<float4*>(w_smem)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
   fence_async_smem();
@@ -183,10 +189,14 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     }
   } else if (warp < 8) {
     // ============================== epilogue ==============================
+    // Work is flattened into (output row, 16-column block) steps.  The ReLU-mask source of step + 1 is in
+    // flight while step is processed (ncu r02: the per-row load was the exposed latency of the kernel), the
+    // per-channel vectors come from shared memory, column sums stay in registers until the CTA is done.
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const bool want_sums = out_stats != nullptr || ep_sums != nullptr;
-    float s0[32], s1[32];                    // this frame-lane's column sums over every row it stores
+    const int CH = Cout >> 4;
+    float s0[32], s1[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
     int li = 0;
@@ -195,64 +205,71 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
       const int fo0 = fc * R, t = tt * FW_TM + row;
       const int h = li & 1;
       const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
-      const bool in_map = t < p.T;
-      for (int r = 0; r < R; ++r) {
-        const long long orow = ((long long)b * p.F + fo0 + r) * p.T + t;
-        float4 src[8];                                 // this frame's row of the ReLU-mask source: in flight during the wait
-        if (ep_src && in_map && t < len_b) {
+      const bool in_map = t < p.T, valid = t < len_b;
+      const bool use_src = ep_src != nullptr && valid;
+      const long long orow0 = ((long long)b * p.F + fo0) * p.T + t;
+      const int nsteps = R * CH;
+      float4 nxt[4];
+      if (use_src) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (4 * q < Cout) src[q] = __ldg(reinterpret_cast<const float4*>(ep_src + orow * Cout + 4 * q));
+        for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(ep_src + orow0 * Cout + 4 * q));
+      }
+      for (int step = 0; step < nsteps; ++step) {
+        const int r = step / CH, cc = (step - r * CH) << 4;
+        const long long obase = (orow0 + (long long)r * p.T) * Cout + cc;
+        float4 cur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+        if (use_src && step + 1 < nsteps) {
+          const int r1 = (step + 1) / CH, c1 = ((step + 1) - r1 * CH) << 4;
+          const float* sp = ep_src + (orow0 + (long long)r1 * p.T) * Cout + c1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(sp + 4 * q));
         }
-        mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < 32; cc += 16) {
-          if (cc >= Cout) break;
-          const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(h * 256 + r * Cout + cc);
-          float v[16];
-          tmem_ld16(ta, v);
-          tmem_st16_zero(ta);                          // the column block is free for the item after next
-          if (in_map) {
+        if (cc == 0) {
+          mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(h * 256 + r * Cout + cc);
+        float v[16];
+        tmem_ld16(ta, v);
+        tmem_st16_zero(ta);                            // the column block is free for the item after next
+        if (in_map) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + cc + j));
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
+            const float4 bb = *reinterpret_cast<const float4*>(&ctl->cvec[0][cc + j]);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            const float4 x = cur[j >> 2];
             if (ep_src) {                              // ReLU / sequence mask of a data-gradient pass
               float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (t < len_b) {
-                sv = src[(cc + j) >> 2];
-                if (ep_scale) {
-                  const float4 es = __ldg(reinterpret_cast<const float4*>(ep_scale + cc + j));
-                  const float4 eh = __ldg(reinterpret_cast<const float4*>(ep_shift + cc + j));
-                  sv.x = fmaf(sv.x, es.x, eh.x); sv.y = fmaf(sv.y, es.y, eh.y);
-                  sv.z = fmaf(sv.z, es.z, eh.z); sv.w = fmaf(sv.w, es.w, eh.w);
-                }
+              if (valid) {
+                const float4 es = *reinterpret_cast<const float4*>(&ctl->cvec[1][cc + j]);
+                const float4 eh = *reinterpret_cast<const float4*>(&ctl->cvec[2][cc + j]);
+                sv.x = fmaf(x.x, es.x, eh.x); sv.y = fmaf(x.y, es.y, eh.y);
+                sv.z = fmaf(x.z, es.z, eh.z); sv.w = fmaf(x.w, es.w, eh.w);
               }
               o.x = sv.x > 0.f ? o.x : 0.f; o.y = sv.y > 0.f ? o.y : 0.f;
               o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
             }
-            *reinterpret_cast<float4*>(out + orow * Cout + cc + j) = o;
-            if (want_sums && t < len_b) {
-              if (out_stats) {                         // next layer's batch statistics: sum, sum of squares
-                s0[cc + j] += o.x; s0[cc + j + 1] += o.y; s0[cc + j + 2] += o.z; s0[cc + j + 3] += o.w;
-                s1[cc + j] = fmaf(o.x, o.x, s1[cc + j]); s1[cc + j + 1] = fmaf(o.y, o.y, s1[cc + j + 1]);
-                s1[cc + j + 2] = fmaf(o.z, o.z, s1[cc + j + 2]); s1[cc + j + 3] = fmaf(o.w, o.w, s1[cc + j + 3]);
-              } else {                                 // batch-norm backward pass 1: sum g, sum g * xhat
-                const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + cc + j));
-                const float4 rs = __ldg(reinterpret_cast<const float4*>(ep_rstd + cc + j));
-                const float4 x = src[(cc + j) >> 2];
-                s0[cc + j] += o.x; s0[cc + j + 1] += o.y; s0[cc + j + 2] += o.z; s0[cc + j + 3] += o.w;
-                s1[cc + j] = fmaf(o.x, (x.x - mu.x) * rs.x, s1[cc + j]);
-                s1[cc + j + 1] = fmaf(o.y, (x.y - mu.y) * rs.y, s1[cc + j + 1]);
-                s1[cc + j + 2] = fmaf(o.z, (x.z - mu.z) * rs.z, s1[cc + j + 2]);
-                s1[cc + j + 3] = fmaf(o.w, (x.w - mu.w) * rs.w, s1[cc + j + 3]);
+            *reinterpret_cast<float4*>(out + obase + j) = o;
+            if (want_sums && valid) {
+              float4 w2 = o;                           // out_stats: sum, sum of squares
+              if (!out_stats) {                        // ep_sums: sum g, sum g * xhat
+                const float4 mu = *reinterpret_cast<const float4*>(&ctl->cvec[3][cc + j]);
+                const float4 rs = *reinterpret_cast<const float4*>(&ctl->cvec[4][cc + j]);
+                w2 = make_float4((x.x - mu.x) * rs.x, (x.y - mu.y) * rs.y, (x.z - mu.z) * rs.z, (x.w - mu.w) * rs.w);
+              }
+              if (cc == 0) {
+                s0[j] += o.x; s0[j + 1] += o.y; s0[j + 2] += o.z; s0[j + 3] += o.w;
+                s1[j] = fmaf(o.x, w2.x, s1[j]); s1[j + 1] = fmaf(o.y, w2.y, s1[j + 1]);
+                s1[j + 2] = fmaf(o.z, w2.z, s1[j + 2]); s1[j + 3] = fmaf(o.w, w2.w, s1[j + 3]);
+              } else {
+                s0[16 + j] += o.x; s0[17 + j] += o.y; s0[18 + j] += o.z; s0[19 + j] += o.w;
+                s1[16 + j] = fmaf(o.x, w2.x, s1[16 + j]); s1[17 + j] = fmaf(o.y, w2.y, s1[17 + j]);
+                s1[18 + j] = fmaf(o.z, w2.z, s1[18 + j]); s1[19 + j] = fmaf(o.w, w2.w, s1[19 + j]);
               }
             }
-          }
           }
         }
       }
@@ -262,8 +279,12 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     }
     if (want_sums) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < Cout) { atomicAdd(&ctl->colacc[0][i], s0[i]); atomicAdd(&ctl->colacc[1][i], s1[i]); }
+      for (int i = 0; i < 32; ++i) {
+        if (i < Cout) {
+          const float a0 = warp_sum(s0[i]), a1 = warp_sum(s1[i]);
+          if (lane == 0) { atomicAdd(&ctl->colacc[0][i], a0); atomicAdd(&ctl->colacc[1][i], a1); }
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = tid - 128;
       if (et < Cout) {

@@ -211,11 +211,15 @@ def test_flatten_layer_batch32_tc_vs_ffma():
 def test_gru_h256_bench_batch_vs_torch(B, bidir, In):
     """the H = 256 recurrence at the benchmark's batch sizes: B = 32 -> clusters of 5 clips with a 2-clip
     tail, B = 33 -> a 3-clip tail; B = 64 bidirectional with the 266-wide tag-conditioned input of the BiCRNN.
-    Forward + input / parameter gradients against torch.nn.GRU on the CPU, ragged lengths."""
+    Forward + input / parameter gradients against torch.nn.GRU on the CPU, ragged lengths.  The output_net is
+    a single linear layer here: with the usual conv -> batch norm -> ReLU head a 1e-5 difference in a
+    pre-activation near zero flips that unit's ReLU mask and moves one clip's gradient by percents -- measured
+    between this package's own fp32 and tf32x3 modes at B = 64 (profiles/r02_gru_b64_relu_flip.txt) -- which
+    says nothing about the recurrence under test."""
     from pb_sed_b200 import modules as M
     torch.manual_seed(B)
     T, H, K = 120, 256, 10
-    out_kw = dict(out_channels=[256, K], kernel_size=1, norm='batch', norm_kwargs={'eps': 1e-3})
+    out_kw = dict(out_channels=[K], kernel_size=1, norm='batch', norm_kwargs={'eps': 1e-3})
     gru = torch.nn.GRU(In, H, num_layers=2, batch_first=True, bidirectional=bidir)
     ora = P.GRU(gru, P.CNN1d(H * (2 if bidir else 1), **out_kw, pre_activation=False, output_layer=True),
                 reverse=not bidir).train()
