@@ -51,8 +51,8 @@ struct __align__(16) FwCtl {
   uint64_t raw_full[FW_NRAW], raw_empty[FW_NRAW], a_full[FW_NA], a_empty[FW_NA];
   uint64_t acc_full[2][FW_MAXR], acc_empty[2];
   uint32_t tmem_base;
-  float colacc[2][32];        // per-CTA column sums of the fused statistics
-  float cvec[5][32];          // per-channel epilogue constants: bias, ep_scale, ep_shift, ep_mean, ep_rstd
+  alignas(16) float colacc[2][32];   // per-CTA column sums of the fused statistics
+  alignas(16) float cvec[5][32];          // per-channel epilogue constants: bias, ep_scale, ep_shift, ep_mean, ep_rstd
 };
 constexpr int FW_STAT_REP = 32;   // global accumulators are replicated: CTAs hash onto them, a fold kernel sums
 
@@ -77,11 +77,11 @@ fwprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_s
     const int tap = tapidx[2 - blk][dt];                  // df = 1 - blk
     const int cin = kb * FW_KB + kc * 4 + e;
     const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)n * w_sn + (long long)cin * w_sc);
-    const float hi = single ? tf32_rn(w) : __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const float hi = tf32_rn(w);
     const long long part = (long long)FW_KCH * N3 * 4;
     const long long base = (long long)(dt * nkb + kb) * 2 * part + ((long long)kc * N3 + np) * 4 + e;
     img[base] = hi;
-    img[base + part] = w - hi;
+    img[base + part] = tf32_rn(w - hi);
   }
 }
 
@@ -173,12 +173,12 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
               *reinterpret_cast<float4*>(hi_base + o) = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
             } else {
               float4 h;
-              h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-              h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-              h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-              h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+              h.x = tf32_rn(x.x);
+              h.y = tf32_rn(x.y);
+              h.z = tf32_rn(x.z);
+              h.w = tf32_rn(x.w);
               *reinterpret_cast<float4*>(hi_base + o) = h;
-              *reinterpret_cast<float4*>(lo_base + o) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+              *reinterpret_cast<float4*>(lo_base + o) = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
             }
           }
           fence_async_smem();

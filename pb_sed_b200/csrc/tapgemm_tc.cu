@@ -72,11 +72,11 @@ wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn
     const int sl = (int)(q / ntaps);
     const int cin = kb * KB + c * 4 + e, cout = sl * N + n;
     const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)cout * w_sn + (long long)cin * w_sc);
-    const float hi = single ? tf32_rn(w) : __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    const float hi = tf32_rn(w);
     const long long blob = ((long long)(sl * ntaps + tap) * nkb + kb) * (2LL * KCH * N * 4);
     const long long off = ((long long)c * N + n) * 4 + e;
     img[blob + off] = hi;
-    img[blob + (long long)KCH * N * 4 + off] = w - hi;
+    img[blob + (long long)KCH * N * 4 + off] = tf32_rn(w - hi);
   }
 }
 
@@ -204,11 +204,11 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
         }
         float4 h;
-        h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        h.x = tf32_rn(x.x);
+        h.y = tf32_rn(x.y);
+        h.z = tf32_rn(x.z);
+        h.w = tf32_rn(x.w);
+        const float4 l = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
         const uint32_t o = (uint32_t)(c * RMAX + r) * 16;
         if (p.single) {
           *reinterpret_cast<float4*>(hi_base + o) = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
@@ -447,12 +447,12 @@ __device__ __forceinline__ void split_store(uint8_t* hi, uint8_t* lo, uint32_t o
     return;
   }
   float4 h;
-  h.x = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  h.y = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-  h.z = __uint_as_float(__float_as_uint(c) & 0xFFFFE000u);
-  h.w = __uint_as_float(__float_as_uint(d) & 0xFFFFE000u);
+  h.x = tf32_rn(a);
+  h.y = tf32_rn(b);
+  h.z = tf32_rn(c);
+  h.w = tf32_rn(d);
   *reinterpret_cast<float4*>(hi + o) = h;
-  *reinterpret_cast<float4*>(lo + o) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+  *reinterpret_cast<float4*>(lo + o) = make_float4(tf32_rn(a - h.x), tf32_rn(b - h.y), tf32_rn(c - h.z), tf32_rn(d - h.w));
 }
 
 constexpr int WG_PROD = 256;              // producer threads (warps 0-7); warp 8 issues the MMAs

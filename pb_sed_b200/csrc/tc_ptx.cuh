@@ -8,7 +8,9 @@
 
 namespace {
 
-// round-to-nearest TF32 (single-pass mode; the split mode truncates because hi + lo is exact either way)
+// round-to-nearest TF32.  The 3xTF32 split uses it for BOTH pieces, hi = rn(x), lo = rn(x - hi): the tensor core
+// truncates the low 13 mantissa bits of what it is given, so a truncating split loses up to 2^-20 |x| in lo; with
+// rounding |x - hi - lo| <= 2^-22 |x| (measured r02: the step's gradient noise vs a float64 oracle drops accordingly)
 __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u);
 }

@@ -28,8 +28,9 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  // both pieces rounded to nearest TF32 (the tensor core would truncate the low 13 bits): |x - hi - lo| <= 2^-22 |x|
+  hi = (__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x00001000u) & 0xFFFFE000u;
 }
 
 constexpr int TT = 64;                       // frames per work unit
