@@ -295,11 +295,16 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     }
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // the whole warp walks the loop (every value is warp-uniform, so descriptors live in uniform registers);
+    // one elected lane issues the tcgen05 instructions
+    {
+      const bool issuer = lane == 0;
       uint32_t idesc[4];
       for (int n = 1; n <= 3; ++n) idesc[n] = make_idesc_tf32(FW_TM, n * Cout);
       const uint32_t W_LBO = (uint32_t)(3 * Cout) * 16, W_PART = FW_KCH * W_LBO;
       const uint32_t w_base = smem_u32(w_smem), a_base = smem_u32(a_smem);
+      const uint32_t w_dt_stride = (uint32_t)(p.nkb * 2) * W_PART;
+      const uint64_t a_d0 = make_desc(0, FW_A_LBO, 128), w_d0 = make_desc(0, W_LBO, 128);
       int it = 0, li = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
         const int fc = item % p.f_chunks;
@@ -316,28 +321,29 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
             mbar_wait(&ctl->a_full[slot], (it / FW_NA) & 1);
             tc_fence_after();
             const uint32_t a_hi = a_base + slot * FW_A_STAGE, a_lo = a_hi + FW_A_PART;
+            const uint32_t w_kb = w_base + (uint32_t)(kb * 2) * W_PART + (uint32_t)(blk0 * Cout) * 16;
+            const uint32_t id = idesc[nblk];
 #pragma unroll
             for (int dt = 0; dt < 3; ++dt) {
-              const uint32_t w_hi = w_base + (uint32_t)((dt * p.nkb + kb) * 2) * W_PART + (uint32_t)(blk0 * Cout) * 16;
-              const uint32_t w_lo = w_hi + W_PART;
+              const uint32_t w_hi = w_kb + (uint32_t)dt * w_dt_stride, w_lo = w_hi + W_PART;
 #pragma unroll
               for (int ks = 0; ks < FW_KB / 8; ++ks) {
                 const uint32_t ao = (uint32_t)dt * 16 + (uint32_t)(ks * 2) * FW_A_LBO, wo = (uint32_t)(ks * 2) * W_LBO;
-                const uint64_t dah = make_desc(a_hi + ao, FW_A_LBO, 128), dal = make_desc(a_lo + ao, FW_A_LBO, 128);
-                const uint64_t dwh = make_desc(w_hi + wo, W_LBO, 128), dwl = make_desc(w_lo + wo, W_LBO, 128);
-                mma_tf32(d, dah, dwh, idesc[nblk], 1u);
-                if (!p.single) {
-                  mma_tf32(d, dal, dwh, idesc[nblk], 1u);
-                  mma_tf32(d, dah, dwl, idesc[nblk], 1u);
+                const uint64_t dah = desc_at(a_d0, a_hi + ao), dwh = desc_at(w_d0, w_hi + wo);
+                if (issuer) mma_tf32(d, dah, dwh, id, 1u);
+                if (issuer && !p.single) {
+                  mma_tf32(d, desc_at(a_d0, a_lo + ao), dwh, id, 1u);
+                  mma_tf32(d, dah, desc_at(w_d0, w_lo + wo), id, 1u);
                 }
               }
             }
-            mma_commit(&ctl->a_empty[slot]);
+            if (issuer) mma_commit(&ctl->a_empty[slot]);
+            __syncwarp();
           }
           // strip f was the last contribution to output row f-1 (and, at the bottom of the map, to row f)
-          if (f - 1 >= fo0) mma_commit(&ctl->acc_full[h][f - 1 - fo0]);
+          if (issuer && f - 1 >= fo0) mma_commit(&ctl->acc_full[h][f - 1 - fo0]);
           if (f == f_hi)
-            for (int r = max(f, fo0); r <= fo0 + R - 1; ++r) mma_commit(&ctl->acc_full[h][r - fo0]);
+            for (int r = max(f, fo0); r <= fo0 + R - 1; ++r) if (issuer) mma_commit(&ctl->acc_full[h][r - fo0]);
         }
       }
     }

@@ -336,6 +336,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, N);
       const uint32_t a_lbo = RMAX * 16, b_lbo = (uint32_t)N * 16;
+      const uint64_t a_d0 = make_desc(0, a_lbo, 128), b_d0 = make_desc(0, b_lbo, 128);
       int it = 0, bt = 0;
       bool first = true;
       for (int kb = 0; kb < p.nkb; ++kb) {
@@ -357,12 +358,11 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
 #pragma unroll
               for (int ks = 0; ks < KB / 8; ++ks) {
                 const uint32_t ao = arow + (uint32_t)(ks * 2) * a_lbo, bo = (uint32_t)(ks * 2) * b_lbo;
-                const uint64_t dah = make_desc(a_hi + ao, a_lbo, 128), dal = make_desc(a_lo + ao, a_lbo, 128);
-                const uint64_t dbh = make_desc(b_hi + bo, b_lbo, 128), dbl = make_desc(b_lo + bo, b_lbo, 128);
+                const uint64_t dah = desc_at(a_d0, a_hi + ao), dbh = desc_at(b_d0, b_hi + bo);
                 mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
                 if (!p.single) {
-                  mma_tf32(d, dal, dbh, idesc, 1u);
-                  mma_tf32(d, dah, dbl, idesc, 1u);
+                  mma_tf32(d, desc_at(a_d0, a_lo + ao), dbh, idesc, 1u);
+                  mma_tf32(d, dah, desc_at(b_d0, b_lo + bo), idesc, 1u);
                 }
               }
             }
@@ -681,6 +681,7 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, p.Nc);
+      const uint64_t z_d0 = make_desc(0, Z_LBO, 128), a_d0 = make_desc(0, A_LBO, 128);
       int it = 0;
       for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
         const int tb = u % t_blocks, gq = u / t_blocks;
@@ -700,12 +701,11 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
 #pragma unroll
             for (int ks = 0; ks < WG_KR / 8; ++ks) {
               const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
-              const uint64_t dzh = make_desc(z_hi + zo, Z_LBO, 128), dzl = make_desc(z_lo + zo, Z_LBO, 128);
-              const uint64_t dah = make_desc(a_hi + ao, A_LBO, 128), dal = make_desc(a_lo + ao, A_LBO, 128);
+              const uint64_t dzh = desc_at(z_d0, z_hi + zo), dah = desc_at(a_d0, a_hi + ao);
               mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
               if (!p.single) {
-                mma_tf32(d, dzl, dah, idesc, 1u);
-                mma_tf32(d, dzh, dal, idesc, 1u);
+                mma_tf32(d, desc_at(z_d0, z_lo + zo), dah, idesc, 1u);
+                mma_tf32(d, dzh, desc_at(a_d0, a_lo + ao), idesc, 1u);
               }
             }
           }
@@ -916,6 +916,7 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, p.Nc);
+      const uint64_t z_d0 = make_desc(0, Z_LBO, 128), a_d0 = make_desc(0, A_LBO, 128);
       int it = 0;
       for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
         const int tb = u % t_blocks, gq = u / t_blocks;
@@ -935,12 +936,11 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
 #pragma unroll
             for (int ks = 0; ks < WG_KR / 8; ++ks) {
               const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
-              const uint64_t dzh = make_desc(z_hi + zo, Z_LBO, 128), dzl = make_desc(z_lo + zo, Z_LBO, 128);
-              const uint64_t dah = make_desc(a_hi + ao, A_LBO, 128), dal = make_desc(a_lo + ao, A_LBO, 128);
+              const uint64_t dzh = desc_at(z_d0, z_hi + zo), dah = desc_at(a_d0, a_hi + ao);
               mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
               if (!p.single) {
-                mma_tf32(d, dzl, dah, idesc, 1u);
-                mma_tf32(d, dzh, dal, idesc, 1u);
+                mma_tf32(d, desc_at(z_d0, z_lo + zo), dah, idesc, 1u);
+                mma_tf32(d, dzh, desc_at(a_d0, a_lo + ao), idesc, 1u);
               }
             }
           }

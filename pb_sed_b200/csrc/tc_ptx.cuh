@@ -92,6 +92,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
+// descriptor arithmetic for the issue loop: the MMA-issuing THREAD is a scalar instruction stream, and rebuilding a
+// descriptor (shifts, masks, 64-bit ors) for each of the 3 x taps x k-steps MMAs of a stage made it the bottleneck
+// of the narrow-N kernels (ncu r02: converters and epilogue waiting on the issuer, tensor pipe 17-30 % busy).
+// Build the constant part once (address field 0) and add the 16-byte-granular address: shared memory is < 256 KB,
+// so (addr >> 4) < 2^14 never carries out of the 14-bit field.
+__device__ __forceinline__ uint64_t desc_at(uint64_t base_desc, uint32_t byte_addr) {
+  return base_desc + (uint64_t)(byte_addr >> 4);
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) [4,6), a/b format TF32 (2)
 // [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
