@@ -295,10 +295,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     }
   } else if (warp == 8) {
     // ============================== MMA issuer ==============================
-    // the whole warp walks the loop (every value is warp-uniform, so descriptors live in uniform registers);
-    // one elected lane issues the tcgen05 instructions
-    {
-      const bool issuer = lane == 0;
+    if (lane == 0) {
       uint32_t idesc[4];
       for (int n = 1; n <= 3; ++n) idesc[n] = make_idesc_tf32(FW_TM, n * Cout);
       const uint32_t W_LBO = (uint32_t)(3 * Cout) * 16, W_PART = FW_KCH * W_LBO;
@@ -330,20 +327,19 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
               for (int ks = 0; ks < FW_KB / 8; ++ks) {
                 const uint32_t ao = (uint32_t)dt * 16 + (uint32_t)(ks * 2) * FW_A_LBO, wo = (uint32_t)(ks * 2) * W_LBO;
                 const uint64_t dah = desc_at(a_d0, a_hi + ao), dwh = desc_at(w_d0, w_hi + wo);
-                if (issuer) mma_tf32(d, dah, dwh, id, 1u);
-                if (issuer && !p.single) {
+                mma_tf32(d, dah, dwh, id, 1u);
+                if (!p.single) {
                   mma_tf32(d, desc_at(a_d0, a_lo + ao), dwh, id, 1u);
                   mma_tf32(d, dah, desc_at(w_d0, w_lo + wo), id, 1u);
                 }
               }
             }
-            if (issuer) mma_commit(&ctl->a_empty[slot]);
-            __syncwarp();
+            mma_commit(&ctl->a_empty[slot]);
           }
           // strip f was the last contribution to output row f-1 (and, at the bottom of the map, to row f)
-          if (issuer && f - 1 >= fo0) mma_commit(&ctl->acc_full[h][f - 1 - fo0]);
+          if (f - 1 >= fo0) mma_commit(&ctl->acc_full[h][f - 1 - fo0]);
           if (f == f_hi)
-            for (int r = max(f, fo0); r <= fo0 + R - 1; ++r) if (issuer) mma_commit(&ctl->acc_full[h][r - fo0]);
+            for (int r = max(f, fo0); r <= fo0 + R - 1; ++r) mma_commit(&ctl->acc_full[h][r - fo0]);
         }
       }
     }
