@@ -35,7 +35,7 @@ constexpr int FW_MAXR = 16;                // output rows per TMEM half (Cout = 
 constexpr uint32_t FW_A_LBO = FW_ROWS * 16;
 constexpr uint32_t FW_A_PART = FW_KCH * FW_A_LBO;      // 8320 B: one hi (or lo) strip stage
 constexpr uint32_t FW_A_STAGE = 2 * FW_A_PART;
-constexpr int FW_THREADS = 320;            // 4 converter warps, 4 epilogue warps, MMA warp, TMA warp
+constexpr int FW_THREADS = 448;            // warps 0-3 converters, 4-7 + 10-13 two epilogue groups, 8 MMA issuer, 9 strip loader
 
 struct FwParams {
   int B, F, T, Cin, Cout;
@@ -106,7 +106,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
     for (int h = 0; h < 2; ++h) {
       for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], 1);
-      mbar_init(&ctl->acc_empty[h], 128);
+      mbar_init(&ctl->acc_empty[h], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -124,7 +124,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
-  if (warp >= 4 && warp < 8) {                // all 512 accumulator columns start at zero: every MMA accumulates
+  if (warp >= 4 && warp < 8) {                // all 512 accumulator columns start at zero: every MMA accumulates (group 0 does it)
     for (int col = 0; col < 512; col += 16) tmem_st16_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + col);
     tmem_wait_st();
   }
@@ -187,18 +187,23 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
         mbar_arrive(&ctl->raw_empty[rs]);              // every channel block of the strip is converted
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 8 || warp >= 10) {
     // ============================== epilogue ==============================
-    // Work is flattened into (output row, 16-column block) steps.  The ReLU-mask source of step + 1 is in
-    // flight while step is processed (ncu r02: the per-row load was the exposed latency of the kernel), the
-    // per-channel vectors come from shared memory, column sums stay in registers until the CTA is done.
-    const int ew = warp & 3;
+    // Work is flattened into (output row, 16-column block) steps, dealt alternately to TWO groups of 4 warps
+    // (ncu r02: one group was busy 83 % of the time while converters and the tensor pipe waited for it): with
+    // Cout = 32 a group owns one 16-column half of every row, with Cout = 16 every other row -- either way a
+    // thread sees ONE fixed 16-channel block, so its column sums are 2 x 16 registers.  The ReLU-mask source of
+    // the group's next step is in flight while the current one is processed; per-channel vectors come from
+    // shared memory.
+    const int ew = warp & 3;                   // TMEM lane quarter (hardware: warp id mod 4)
+    const int grp = warp >= 10 ? 1 : 0;
     const int row = ew * 32 + lane;
     const bool want_sums = out_stats != nullptr || ep_sums != nullptr;
     const int CH = Cout >> 4;
-    float s0[32], s1[32];
+    const int cc = CH == 2 ? grp * 16 : 0;     // this thread's channel block
+    float s0[16], s1[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+    for (int i = 0; i < 16; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
     int li = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
       const int fc = item % p.f_chunks, tt = (item / p.f_chunks) % p.t_tiles, b = item / (p.f_chunks * p.t_tiles);
@@ -210,26 +215,24 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
       const long long orow0 = ((long long)b * p.F + fo0) * p.T + t;
       const int nsteps = R * CH;
       float4 nxt[4];
-      if (use_src) {
+      if (use_src && grp < nsteps) {
+        const float* sp = ep_src + (orow0 + (long long)(grp / CH) * p.T) * Cout + cc;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(ep_src + orow0 * Cout + 4 * q));
+        for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(sp + 4 * q));
       }
-      for (int step = 0; step < nsteps; ++step) {
-        const int r = step / CH, cc = (step - r * CH) << 4;
+      for (int step = grp; step < nsteps; step += 2) {
+        const int r = step / CH;
         const long long obase = (orow0 + (long long)r * p.T) * Cout + cc;
         float4 cur[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
-        if (use_src && step + 1 < nsteps) {
-          const int r1 = (step + 1) / CH, c1 = ((step + 1) - r1 * CH) << 4;
-          const float* sp = ep_src + (orow0 + (long long)r1 * p.T) * Cout + c1;
+        if (use_src && step + 2 < nsteps) {
+          const float* sp = ep_src + (orow0 + (long long)((step + 2) / CH) * p.T) * Cout + cc;
 #pragma unroll
           for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(sp + 4 * q));
         }
-        if (cc == 0) {
-          mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
-          tc_fence_after();
-        }
+        mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
+        tc_fence_after();
         const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(h * 256 + r * Cout + cc);
         float v[16];
         tmem_ld16(ta, v);
@@ -260,15 +263,9 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
                 const float4 rs = *reinterpret_cast<const float4*>(&ctl->cvec[4][cc + j]);
                 w2 = make_float4((x.x - mu.x) * rs.x, (x.y - mu.y) * rs.y, (x.z - mu.z) * rs.z, (x.w - mu.w) * rs.w);
               }
-              if (cc == 0) {
-                s0[j] += o.x; s0[j + 1] += o.y; s0[j + 2] += o.z; s0[j + 3] += o.w;
-                s1[j] = fmaf(o.x, w2.x, s1[j]); s1[j + 1] = fmaf(o.y, w2.y, s1[j + 1]);
-                s1[j + 2] = fmaf(o.z, w2.z, s1[j + 2]); s1[j + 3] = fmaf(o.w, w2.w, s1[j + 3]);
-              } else {
-                s0[16 + j] += o.x; s0[17 + j] += o.y; s0[18 + j] += o.z; s0[19 + j] += o.w;
-                s1[16 + j] = fmaf(o.x, w2.x, s1[16 + j]); s1[17 + j] = fmaf(o.y, w2.y, s1[17 + j]);
-                s1[18 + j] = fmaf(o.z, w2.z, s1[18 + j]); s1[19 + j] = fmaf(o.w, w2.w, s1[19 + j]);
-              }
+              s0[j] += o.x; s0[j + 1] += o.y; s0[j + 2] += o.z; s0[j + 3] += o.w;
+              s1[j] = fmaf(o.x, w2.x, s1[j]); s1[j + 1] = fmaf(o.y, w2.y, s1[j + 1]);
+              s1[j + 2] = fmaf(o.z, w2.z, s1[j + 2]); s1[j + 3] = fmaf(o.w, w2.w, s1[j + 3]);
             }
           }
         }
@@ -279,15 +276,13 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     }
     if (want_sums) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < Cout) {
-          const float a0 = warp_sum(s0[i]), a1 = warp_sum(s1[i]);
-          if (lane == 0) { atomicAdd(&ctl->colacc[0][i], a0); atomicAdd(&ctl->colacc[1][i], a1); }
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float a0 = warp_sum(s0[i]), a1 = warp_sum(s1[i]);
+        if (lane == 0) { atomicAdd(&ctl->colacc[0][cc + i], a0); atomicAdd(&ctl->colacc[1][cc + i], a1); }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = tid - 128;
-      if (et < Cout) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int et = tid - 128;                 // group 0's threads flush
+      if (et >= 0 && et < Cout) {
         double* dst = (out_stats ? out_stats : ep_sums) + ((long long)(blockIdx.x % FW_STAT_REP) * Cout + et) * 2;
         atomicAdd(dst, (double)ctl->colacc[0][et]);
         atomicAdd(dst + 1, (double)ctl->colacc[1][et]);
