@@ -35,7 +35,7 @@ constexpr int FW_MAXR = 16;                // output rows per TMEM half (Cout = 
 constexpr uint32_t FW_A_LBO = FW_ROWS * 16;
 constexpr uint32_t FW_A_PART = FW_KCH * FW_A_LBO;      // 8320 B: one hi (or lo) strip stage
 constexpr uint32_t FW_A_STAGE = 2 * FW_A_PART;
-constexpr int FW_THREADS = 448;            // warps 0-3 converters, 4-7 + 10-13 two epilogue groups, 8 MMA issuer, 9 strip loader
+constexpr int FW_THREADS = 512;            // warps 0-3 converters, 4-7 + 10-13 two epilogue groups, 8 / 14 / 15 MMA issuers, 9 strip loader
 
 struct FwParams {
   int B, F, T, Cin, Cout;
@@ -103,9 +103,10 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
 
   if (tid == 0) {
     for (int i = 0; i < p.nraw; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], 128); }
-    for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], 1); }
+    const uint32_t n_issuers = p.single ? 1u : 3u;
+    for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], n_issuers); }
     for (int h = 0; h < 2; ++h) {
-      for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], 1);
+      for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], n_issuers);
       mbar_init(&ctl->acc_empty[h], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,7 +188,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
         mbar_arrive(&ctl->raw_empty[rs]);              // every channel block of the strip is converted
       }
     }
-  } else if (warp < 8 || warp >= 10) {
+  } else if (warp < 8 || (warp >= 10 && warp < 14)) {
     // ============================== epilogue ==============================
     // Work is flattened into (output row, 16-column block) steps, dealt alternately to TWO groups of 4 warps
     // (ncu r02: one group was busy 83 % of the time while converters and the tensor pipe waited for it): with
@@ -288,9 +289,14 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
         atomicAdd(dst + 1, (double)ctl->colacc[1][et]);
       }
     }
-  } else if (warp == 8) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+  } else if (warp == 8 || warp >= 14) {
+    // ============================== MMA issuers ==============================
+    // One thread feeding tcgen05.mma spends ~100 cycles of dependent scalar work per instruction (ncu r02: the
+    // issuing warp never idles while the tensor pipe is 17-30 % busy), far more than an M128 x N48 x K8 MMA runs.
+    // The three passes of the split (hi*hi, lo*hi, hi*lo) are therefore issued by THREE threads in three warps,
+    // each with fixed operand images; accumulation order is irrelevant, every barrier counts all issuers.
+    const int pass = warp == 8 ? 0 : warp - 13;               // 0: hi*hi, 1: lo*hi, 2: hi*lo
+    if (lane == 0 && (pass == 0 || !p.single)) {
       uint32_t idesc[4];
       for (int n = 1; n <= 3; ++n) idesc[n] = make_idesc_tf32(FW_TM, n * Cout);
       const uint32_t W_LBO = (uint32_t)(3 * Cout) * 16, W_PART = FW_KCH * W_LBO;
@@ -321,12 +327,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
 #pragma unroll
               for (int ks = 0; ks < FW_KB / 8; ++ks) {
                 const uint32_t ao = (uint32_t)dt * 16 + (uint32_t)(ks * 2) * FW_A_LBO, wo = (uint32_t)(ks * 2) * W_LBO;
-                const uint64_t dah = desc_at(a_d0, a_hi + ao), dwh = desc_at(w_d0, w_hi + wo);
-                mma_tf32(d, dah, dwh, id, 1u);
-                if (!p.single) {
-                  mma_tf32(d, desc_at(a_d0, a_lo + ao), dwh, id, 1u);
-                  mma_tf32(d, dah, desc_at(w_d0, w_lo + wo), id, 1u);
-                }
+                mma_tf32(d, desc_at(a_d0, (pass == 1 ? a_lo : a_hi) + ao), desc_at(w_d0, (pass == 2 ? w_lo : w_hi) + wo), id, 1u);
               }
             }
             mma_commit(&ctl->a_empty[slot]);
