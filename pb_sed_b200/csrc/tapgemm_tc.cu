@@ -352,19 +352,17 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
             tc_fence_after();
             const uint32_t b_hi = smem_u32(b_smem + bslot * B_STAGE), b_lo = b_hi + B_PART;
             const int dt = p.g_dt[g][j];
-            // consecutive MMAs go to DIFFERENT accumulators (row tiles): an MMA into the columns its predecessor
-            // is still accumulating into waits for it (measured r02: ~115 cycles per dependent tcgen05.mma whatever
-            // its N), independent accumulators overlap in the tensor pipe
+            for (int mt = 0; mt < mt_count; ++mt) {
+              const uint32_t d = tmem_base + (uint32_t)(mt * N);
+              const uint32_t arow = (uint32_t)(mt * TILE_M + dt + HALO) * 16;
 #pragma unroll
-            for (int ks = 0; ks < KB / 8; ++ks) {
-              const uint32_t bo = (uint32_t)(ks * 2) * b_lbo;
-              const uint64_t dbh = desc_at(b_d0, b_hi + bo), dbl = desc_at(b_d0, b_lo + bo);
-              for (int pass = 0; pass < (p.single ? 1 : 3); ++pass) {
-                for (int mt = 0; mt < mt_count; ++mt) {
-                  const uint32_t d = tmem_base + (uint32_t)(mt * N);
-                  const uint32_t ao = (uint32_t)(mt * TILE_M + dt + HALO) * 16 + (uint32_t)(ks * 2) * a_lbo;
-                  mma_tf32(d, desc_at(a_d0, (pass == 1 ? a_lo : a_hi) + ao), pass == 2 ? dbl : dbh, idesc,
-                           (first && ks == 0 && pass == 0) ? 0u : 1u);
+              for (int ks = 0; ks < KB / 8; ++ks) {
+                const uint32_t ao = arow + (uint32_t)(ks * 2) * a_lbo, bo = (uint32_t)(ks * 2) * b_lbo;
+                const uint64_t dah = desc_at(a_d0, a_hi + ao), dbh = desc_at(b_d0, b_hi + bo);
+                mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+                if (!p.single) {
+                  mma_tf32(d, desc_at(a_d0, a_lo + ao), dbh, idesc, 1u);
+                  mma_tf32(d, dah, desc_at(b_d0, b_lo + bo), idesc, 1u);
                 }
               }
             }
@@ -697,18 +695,17 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
           tc_fence_after();
           const uint32_t z_hi = smem_u32(smem_raw + slot * STAGE), z_lo = z_hi + Z_PART;
           const uint32_t a_hi = z_lo + Z_PART, a_lo = a_hi + A_PART;
-          // consecutive MMAs alternate between the tap accumulators: dependent tcgen05.mma into the same TMEM
-          // columns serialise (~115 cycles each, measured r02), independent ones overlap
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
+            const int dt = p.g_dt[g][j];
 #pragma unroll
-          for (int ks = 0; ks < WG_KR / 8; ++ks) {
-            const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO;
-            const uint64_t dzh = desc_at(z_d0, z_hi + zo), dzl = desc_at(z_d0, z_lo + zo);
-            for (int pass = 0; pass < (p.single ? 1 : 3); ++pass) {
-              for (int j = 0; j < ntap; ++j) {
-                const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
-                const uint32_t ao = (uint32_t)(2 * ks + p.g_dt[g][j] + 1) * A_LBO;
-                mma_tf32(d, pass == 1 ? dzl : dzh, desc_at(a_d0, (pass == 2 ? a_lo : a_hi) + ao), idesc,
-                         (it == 0 && ks == 0 && pass == 0) ? 0u : 1u);
+            for (int ks = 0; ks < WG_KR / 8; ++ks) {
+              const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
+              const uint64_t dzh = desc_at(z_d0, z_hi + zo), dah = desc_at(a_d0, a_hi + ao);
+              mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+              if (!p.single) {
+                mma_tf32(d, desc_at(z_d0, z_lo + zo), dah, idesc, 1u);
+                mma_tf32(d, dzh, desc_at(a_d0, a_lo + ao), idesc, 1u);
               }
             }
           }
@@ -933,18 +930,17 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
           tc_fence_after();
           const uint32_t z_hi = smem_u32(smem_raw + slot * STAGE), z_lo = z_hi + Z_PART;
           const uint32_t a_hi = z_lo + Z_PART, a_lo = a_hi + A_PART;
-          // consecutive MMAs alternate between the tap accumulators: dependent tcgen05.mma into the same TMEM
-          // columns serialise (~115 cycles each, measured r02), independent ones overlap
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
+            const int dt = p.g_dt[g][j];
 #pragma unroll
-          for (int ks = 0; ks < WG_KR / 8; ++ks) {
-            const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO;
-            const uint64_t dzh = desc_at(z_d0, z_hi + zo), dzl = desc_at(z_d0, z_lo + zo);
-            for (int pass = 0; pass < (p.single ? 1 : 3); ++pass) {
-              for (int j = 0; j < ntap; ++j) {
-                const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
-                const uint32_t ao = (uint32_t)(2 * ks + p.g_dt[g][j] + 1) * A_LBO;
-                mma_tf32(d, pass == 1 ? dzl : dzh, desc_at(a_d0, (pass == 2 ? a_lo : a_hi) + ao), idesc,
-                         (it == 0 && ks == 0 && pass == 0) ? 0u : 1u);
+            for (int ks = 0; ks < WG_KR / 8; ++ks) {
+              const uint32_t zo = (uint32_t)(2 * ks) * Z_LBO, ao = (uint32_t)(2 * ks + dt + 1) * A_LBO;
+              const uint64_t dzh = desc_at(z_d0, z_hi + zo), dah = desc_at(a_d0, a_hi + ao);
+              mma_tf32(d, dzh, dah, idesc, (it == 0 && ks == 0) ? 0u : 1u);
+              if (!p.single) {
+                mma_tf32(d, desc_at(z_d0, z_lo + zo), dah, idesc, 1u);
+                mma_tf32(d, dzh, desc_at(a_d0, a_lo + ao), idesc, 1u);
               }
             }
           }
