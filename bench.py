@@ -369,7 +369,9 @@ def run_gpu(args):
             'metric': 'fbcrnn_train_clips_per_sec', 'value': value, 'unit': '10s-clips/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': scaling, 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
-                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate; reduced precision >= bf16 mantissa)'}[args.precision],
+                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate; reduced precision >= bf16 mantissa)',
+                      'bf16': 'bf16 (conv-stack activations + gradients stored as bf16 in HBM; tcgen05 products of bf16 activations with '
+                              'TF32-rounded weights, fp32 accumulate; fp32 master weights, statistics, GRU, optimizer)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': ('BASELINE configs[4] shape: ' if stream_mode else '') + workload_name(args, B),
                        'global_batch': gB, 'parallelism': f'dp{world}', 'precision': args.precision,
@@ -557,7 +559,8 @@ def run_bicrnn_infer(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': float(ms) / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
-                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate)'}[args.precision],
+                      'tf32': 'tf32 single pass (tcgen05, fp32 accumulate)',
+                      'bf16': 'bf16 activation maps in HBM, fp32 accumulate'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': f'BASELINE configs[3]: strong_label tag-conditioned BiCRNN inference, batch {B}/GPU of '
                                    '10 s / 16 kHz clips, eval mode, raw audio -> frame scores -> sequence mask + '
@@ -578,7 +581,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
-    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--precision', default='tf32x3', choices=['fp32', 'tf32x3', 'tf32', 'bf16'],
+                    help="tf32x3 = fp32-equivalent split (headline); tf32 = one TF32 pass; bf16 = bf16 activation maps in HBM, "
+                         "bf16 x bf16 products, fp32 accumulation (BASELINE configs[2] / [4])")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--num-events', type=int, default=NUM_EVENTS, help='K (527 = AudioSet, training.py:128)')
     ap.add_argument('--strong-weight', type=float, default=1., help='strong_fwd_bwd_loss_weight (0 for AudioSet, :151)')

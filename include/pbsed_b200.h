@@ -29,6 +29,8 @@ extern "C" {
 #define PBSED_EINVAL   (-1)   /* bad argument / unsupported shape            */
 #define PBSED_EWORKSPACE (-2) /* workspace too small                         */
 #define PBSED_MAX_TAPS 16
+#define PBSED_F32  0          /* activation storage types (the *_dtype arguments below) */
+#define PBSED_BF16 1
 
 /* library identification: returns the ABI version (bumped on signature change) */
 int pbsed_abi_version(void);
@@ -130,6 +132,11 @@ typedef struct {
   int no_input_mask; /* 1: seq_len does NOT zero the loaded operand (a bare conv reads its input unmasked,
                         the reference masks inside Normalization only); seq_len still masks the fused
                         statistics / epilogue */
+  int in_dtype;      /* storage type of `in`:  PBSED_F32 (0) or PBSED_BF16 (1).  Activation maps of the conv
+                        stacks (and their gradients) may live in HBM as bf16 (BASELINE "bf16" configurations);
+                        arithmetic and accumulation stay as `precision` says, weights / statistics are fp32 */
+  int out_dtype;     /* storage type of `out` and `ep_src` (pbsed_tapgemm) / of `dout` (pbsed_tapgemm_wgrad).
+                        bf16 maps are handled by the tensor-core kernels only (channel counts they accept) */
 } pbsed_tapgemm_desc;
 
 int pbsed_tapgemm(const pbsed_tapgemm_desc* d_host,
@@ -158,10 +165,12 @@ int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d_host,
 
 /* ---------------------------------------------------------------------------
  * Normalisation / pooling helpers (padertorch Normalization + max_pool2d)
+ * *_dtype: storage type of the activation maps (x, y, g, dx ...; PBSED_F32 / PBSED_BF16); a `float*` that is
+ * declared bf16 points at 2-byte elements.  Statistics, sums and per-channel vectors are always fp32 / fp64.
  */
 /* stats[idx][0..1] += sum, sum of squares over valid rows; idx = c or f*C+c (per_f). double[.][2] */
 int pbsed_channel_stats(const float* x, int B, int F, int T, int C, int per_f,
-                        const int* seq_len, double* stats, void* stream);
+                        const int* seq_len, double* stats, int act_dtype, void* stream);
 /* batch statistics -> affine used on load, and running-statistics update.
  *   n = count (valid rows per channel), mean = s/n, var = ss/n - mean^2 (biased)
  *   scale = gamma * rsqrt(var+eps); shift = beta - mean*scale; save_mean/save_rstd for backward.
@@ -181,9 +190,10 @@ int pbsed_norm_finalize(const double* stats, double count, int nch,
  * out_stats (nullable, double[C][2]): += per-channel sum / sum of squares of the POOLED map over frames
  * t < seq_len[b] -- the next layer's batch statistics, fused into the pooling pass. */
 int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool,
-                    float* y, uint8_t* idx, const int* seq_len, double* out_stats, void* stream);
+                    float* y, uint8_t* idx, const int* seq_len, double* out_stats,
+                    int in_dtype, int out_dtype, void* stream);
 int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C, int pool,
-                        float* dx, void* stream);
+                        float* dx, int in_dtype, int out_dtype, void* stream);
 /* batch-norm backward, two passes.  g = gradient w.r.t. the normalised+affine output (already
  * multiplied by the ReLU mask), x = the layer input the statistics were taken on.
  *   pass 1: sums[idx][0] += sum g ; sums[idx][1] += sum g * xhat       (valid rows only)
@@ -193,11 +203,11 @@ int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T
  *           dgamma / dbeta nullable (data-parallel: the replica adds its LOCAL sums itself). */
 int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int F, int T, int C, int per_f,
                           const int* seq_len, const float* save_mean, const float* save_rstd,
-                          double* sums, void* stream);
+                          double* sums, int act_dtype, void* stream);
 int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F, int T, int C, int per_f,
                          const int* seq_len, const float* save_mean, const float* save_rstd,
                          const float* gamma, const double* sums, double count,
-                         float* dx, float* dgamma, float* dbeta, void* stream);
+                         float* dx, float* dgamma, float* dbeta, int act_dtype, void* stream);
 /* out = [add +] x  with the tag condition broadcast (B,K) -> extra channels; see pbsed_concat_cond */
 /* rows (B,F,T,C) <- concat( x (B,F,T,C0), cond (B,K) broadcast over f,t )  (strong_label/crnn.py:86-91) */
 int pbsed_concat_cond(const float* x, const float* cond, int B, int F, int T, int C0, int K,

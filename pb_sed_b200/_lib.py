@@ -23,7 +23,7 @@ class TapGemmDesc(ctypes.Structure):
         ('relu', ctypes.c_int), ('per_f', ctypes.c_int),
         ('w_tap_stride', ctypes.c_longlong), ('w_sn', ctypes.c_longlong), ('w_sc', ctypes.c_longlong),
         ('in_stride', ctypes.c_int), ('out_stride', ctypes.c_int), ('precision', ctypes.c_int),
-        ('no_input_mask', ctypes.c_int),
+        ('no_input_mask', ctypes.c_int), ('in_dtype', ctypes.c_int), ('out_dtype', ctypes.c_int),
     ]
 
 

@@ -12,6 +12,7 @@ struct Cin1Params {
   int df[PBSED_MAX_TAPS], dt[PBSED_MAX_TAPS];
   int relu;
   int out_stride;
+  int out_bf16;          // `out` (forward) / `dout` (weight gradient) is stored as bf16
 };
 
 __device__ __forceinline__ float cin1_load(const float* __restrict__ in, const Cin1Params& p, int b, int f,
@@ -48,10 +49,10 @@ conv_cin1_fwd_kernel(Cin1Params p, const float* __restrict__ in, const float* __
 #pragma unroll
     for (int n = 0; n < COUT; ++n) acc[n] = fmaf(a, ws[tap][n], acc[n]);
   }
-  float* dst = out + (((long long)b * p.F_out + fo) * p.T + t) * p.out_stride;
+  const long long o = (((long long)b * p.F_out + fo) * p.T + t) * p.out_stride;
 #pragma unroll
   for (int n = 0; n < COUT; n += 4)
-    *reinterpret_cast<float4*>(dst + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+    st_act4(out, o + n, make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]), p.out_bf16);
 }
 
 // dW[tap][n] += sum_rows dout[row][n] * a[row + off(tap)];  dbias[n] += sum_rows dout[row][n]
@@ -87,9 +88,9 @@ conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* 
       strip[i] = cin1_load(in, p, b, fo + df_min + r, tt + dt_min, len_b, sc, sh, affine);
     }
     __syncthreads();
-    const float* z = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + n;
+    const long long z0 = ((long long)b * p.F_out + fo) * p.T * p.out_stride + n;
     for (int t = rl; t < len_out; t += RL) {
-      const float dz = __ldg(z + (long long)t * p.out_stride);
+      const float dz = ld_act1(dout, z0 + (long long)t * p.out_stride, p.out_bf16);
       bsum += dz;
 #pragma unroll
       for (int tap = 0; tap < PBSED_MAX_TAPS; ++tap) {
@@ -116,7 +117,7 @@ static bool cin1_ok(const pbsed_tapgemm_desc* d) {
   const int out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
   return d->Cin == 1 && in_stride == 1 && (d->Cout == 16 || d->Cout == 32) && out_stride % 4 == 0 &&
          d->w_sn == 1 && d->w_sc == 1 && d->w_tap_stride == d->Cout && d->per_f == 0 &&
-         d->F_out <= 65535 && d->B <= 65535;
+         d->F_out <= 65535 && d->B <= 65535 && d->in_dtype == PBSED_F32;
 }
 
 static void cin1_fill(const pbsed_tapgemm_desc* d, Cin1Params& p) {
@@ -124,6 +125,7 @@ static void cin1_fill(const pbsed_tapgemm_desc* d, Cin1Params& p) {
   for (int i = 0; i < d->ntaps; ++i) { p.df[i] = d->df[i]; p.dt[i] = d->dt[i]; }
   p.relu = d->relu;
   p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
+  p.out_bf16 = d->out_dtype == PBSED_BF16;
 }
 
 int conv_cin1_fwd_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,

@@ -67,9 +67,9 @@ colreduce_kernel(const float* __restrict__ a, const float* __restrict__ x, int F
 // float4 variant (C % 4 == 0, C <= 1024): thread = (row lane, channel quad); 4 independent rows in flight
 template <int MODE>
 __global__ void __launch_bounds__(256)
-colreduce4_kernel(const float* __restrict__ a, const float* __restrict__ x, int F, int T, int C,
+colreduce4_kernel(const void* __restrict__ a, const void* __restrict__ x, int F, int T, int C,
                   int per_f, const int* __restrict__ seq_len, const float* __restrict__ mean,
-                  const float* __restrict__ rstd, double* __restrict__ out, int t_chunk) {
+                  const float* __restrict__ rstd, double* __restrict__ out, int t_chunk, int bf) {
   __shared__ float4 red[2][256];
   const int tid = threadIdx.x;
   const int g = blockIdx.x;
@@ -89,8 +89,7 @@ colreduce4_kernel(const float* __restrict__ a, const float* __restrict__ x, int 
       mu = __ldg(reinterpret_cast<const float4*>(mean + idx_base));
       rs = __ldg(reinterpret_cast<const float4*>(rstd + idx_base));
     }
-    const float4* ap = reinterpret_cast<const float4*>(a + (long long)g * T * C) + q;
-    const float4* xp = MODE == 1 ? reinterpret_cast<const float4*>(x + (long long)g * T * C) + q : nullptr;
+    const long long e0 = (long long)g * T * C + 4 * q;        // element index of (row group, frame 0, this quad)
     for (int t = t0 + lane_r; t < t1; t += 4 * rl) {
       float4 v[4], w[4];
 #pragma unroll
@@ -98,8 +97,8 @@ colreduce4_kernel(const float* __restrict__ a, const float* __restrict__ x, int 
         const int tt = t + k * rl;
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f); w[k] = mu;
         if (tt < t1) {
-          v[k] = __ldg(ap + (long long)tt * C4);
-          if (MODE == 1) w[k] = __ldg(xp + (long long)tt * C4);
+          v[k] = ld_act4(a, e0 + (long long)tt * C, bf);
+          if (MODE == 1) w[k] = ld_act4(x, e0 + (long long)tt * C, bf);
         }
       }
 #pragma unroll
@@ -144,13 +143,15 @@ static int stats_t_chunk(int B, int F, int T) {
 }
 
 extern "C" int pbsed_channel_stats(const float* x, int B, int F, int T, int C, int per_f,
-                                   const int* seq_len, double* stats, void* stream) {
+                                   const int* seq_len, double* stats, int act_dtype, void* stream) {
   if (!x || !stats || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
   const int tc = stats_t_chunk(B, F, T);
   dim3 grid(B * F, cdiv(T, tc));
   if ((C & 3) == 0 && C <= 1024 && (((uintptr_t)x) & 15) == 0)
     colreduce4_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
-                                                                 nullptr, nullptr, stats, tc);
+                                                                 nullptr, nullptr, stats, tc, act_dtype);
+  else if (act_dtype != PBSED_F32)
+    return PBSED_EINVAL;                      // bf16 maps: channel counts that are multiples of 4 only
   else
     colreduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(x, nullptr, F, T, C, per_f, seq_len,
                                                                 nullptr, nullptr, stats, tc);
@@ -159,13 +160,15 @@ extern "C" int pbsed_channel_stats(const float* x, int B, int F, int T, int C, i
 
 extern "C" int pbsed_norm_bwd_reduce(const float* g, const float* x, int B, int F, int T, int C,
                                      int per_f, const int* seq_len, const float* save_mean,
-                                     const float* save_rstd, double* sums, void* stream) {
+                                     const float* save_rstd, double* sums, int act_dtype, void* stream) {
   if (!g || !x || !sums || !save_mean || !save_rstd || B < 1 || F < 1 || T < 1 || C < 1) return PBSED_EINVAL;
   const int tc = stats_t_chunk(B, F, T);
   dim3 grid(B * F, cdiv(T, tc));
   if ((C & 3) == 0 && C <= 1024 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)save_mean) | ((uintptr_t)save_rstd)) & 15) == 0)
     colreduce4_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
-                                                                 save_mean, save_rstd, sums, tc);
+                                                                 save_mean, save_rstd, sums, tc, act_dtype);
+  else if (act_dtype != PBSED_F32)
+    return PBSED_EINVAL;
   else
     colreduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g, x, F, T, C, per_f, seq_len,
                                                                 save_mean, save_rstd, sums, tc);
@@ -295,11 +298,11 @@ __device__ __forceinline__ NbaCoef nba_coef(const float4* __restrict__ mean, con
 }
 
 __global__ void __launch_bounds__(256)
-norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ x, int F, int T, int C4,
+norm_bwd_apply4_kernel(const void* __restrict__ g, const void* __restrict__ x, int F, int T, int C4,
                        int per_f, const int* __restrict__ seq_len, const float4* __restrict__ mean,
                        const float4* __restrict__ rstd, const float4* __restrict__ gamma,
-                       const double* __restrict__ sums, float inv_n, float4* __restrict__ dx,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch) {
+                       const double* __restrict__ sums, float inv_n, void* __restrict__ dx,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch, int bf) {
   if (inv_n <= 0.f) inv_n = (float)(1.0 / sums[2 * nch]);   // device-side count
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;       // multiple of C4 (256 % C4 == 0)
@@ -325,7 +328,7 @@ norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ 
         const int b = (int)(gq / F);
         const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
         ok[u] = t < len_b;
-        if (ok[u]) { gv[u] = __ldg(g + row * C4 + q); xv[u] = __ldg(x + row * C4 + q); }
+        if (ok[u]) { gv[u] = ld_act4(g, 4 * (row * C4 + q), bf); xv[u] = ld_act4(x, 4 * (row * C4 + q), bf); }
       }
     }
 #pragma unroll
@@ -340,7 +343,7 @@ norm_bwd_apply4_kernel(const float4* __restrict__ g, const float4* __restrict__ 
         r.z = fmaf(k.a.z, gv[u].z, fmaf(k.bx.z, xv[u].z, k.c0.z));
         r.w = fmaf(k.a.w, gv[u].w, fmaf(k.bx.w, xv[u].w, k.c0.w));
       }
-      dx[row * C4 + q] = r;
+      st_act4(dx, 4 * (row * C4 + q), r, bf);
     }
   }
   if (blockIdx.x == 0 && dgamma) {
@@ -355,7 +358,7 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
                                     int per_f, const int* seq_len, const float* save_mean,
                                     const float* save_rstd, const float* gamma, const double* sums,
                                     double count, float* dx, float* dgamma, float* dbeta,
-                                    void* stream) {
+                                    int act_dtype, void* stream) {
   if (!g || !x || !sums || !dx || !save_mean || !save_rstd) return PBSED_EINVAL;
   if ((dgamma == nullptr) != (dbeta == nullptr)) return PBSED_EINVAL;
   const float inv_count = count > 0. ? (float)(1.0 / count) : 0.f;   // <= 0: count = sums[2*nch] on the device
@@ -367,12 +370,13 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
     int blocks4 = (int)((total4 + 255) / 256);
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;
     norm_bwd_apply4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(x), F, T, C / 4, per_f, seq_len,
+        g, x, F, T, C / 4, per_f, seq_len,
         reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
-        reinterpret_cast<const float4*>(gamma), sums, inv_count, reinterpret_cast<float4*>(dx),
-        dgamma, dbeta, total4, nch);
+        reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
+        dgamma, dbeta, total4, nch, act_dtype);
     return pbsed_after_launch();
   }
+  if (act_dtype != PBSED_F32) return PBSED_EINVAL;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   norm_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
@@ -430,21 +434,21 @@ maxpool_f_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ i
 // the same channel quad for its whole loop and the sums live in registers until the end.
 template <bool STATS>
 __global__ void __launch_bounds__(256)
-maxpool2_f4_kernel(const float4* __restrict__ x, int Fo, long long TC4, float4* __restrict__ y,
+maxpool2_f4_kernel(const void* __restrict__ x, int Fo, long long TC4, void* __restrict__ y,
                    uchar4* __restrict__ idx, long long total4, int C4, const int* __restrict__ seq_len,
-                   double* __restrict__ stats) {
+                   double* __restrict__ stats, int bf_in, int bf_out) {
   __shared__ float red[2][1024];
   const long long stride = (long long)gridDim.x * blockDim.x;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
     const long long tc = i % TC4, gq = i / TC4;         // gq = b * Fo + fo
-    const float4 a = __ldg(x + (2 * gq) * TC4 + tc), c = __ldg(x + (2 * gq + 1) * TC4 + tc);
+    const float4 a = ld_act4(x, 4 * ((2 * gq) * TC4 + tc), bf_in), c = ld_act4(x, 4 * ((2 * gq + 1) * TC4 + tc), bf_in);
     float4 r; uchar4 k;
     k.x = (c.x > a.x || c.x != c.x) ? 1 : 0; r.x = k.x ? c.x : a.x;
     k.y = (c.y > a.y || c.y != c.y) ? 1 : 0; r.y = k.y ? c.y : a.y;
     k.z = (c.z > a.z || c.z != c.z) ? 1 : 0; r.z = k.z ? c.z : a.z;
     k.w = (c.w > a.w || c.w != c.w) ? 1 : 0; r.w = k.w ? c.w : a.w;
-    y[i] = r;
+    st_act4(y, 4 * i, r, bf_out);
     if (idx) idx[i] = k;
     if (STATS) {
       const int t = (int)(tc / C4);
@@ -472,21 +476,21 @@ maxpool2_f4_kernel(const float4* __restrict__ x, int Fo, long long TC4, float4* 
   }
 }
 __global__ void __launch_bounds__(256)
-maxpool2_f4_bwd_kernel(const float4* __restrict__ dy, const uchar4* __restrict__ idx, long long TC4,
-                       float4* __restrict__ dx, long long total4_out) {
+maxpool2_f4_bwd_kernel(const void* __restrict__ dy, const uchar4* __restrict__ idx, long long TC4,
+                       void* __restrict__ dx, long long total4_out, int bf_in, int bf_out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4_out; i += stride) {
     const long long tc = i % TC4, gq = i / TC4;
-    const float4 g = __ldg(dy + i);
+    const float4 g = ld_act4(dy, 4 * i, bf_in);
     const uchar4 k = idx[i];
     float4 lo = z, hi = z;
     if (k.x) hi.x = g.x; else lo.x = g.x;
     if (k.y) hi.y = g.y; else lo.y = g.y;
     if (k.z) hi.z = g.z; else lo.z = g.z;
     if (k.w) hi.w = g.w; else lo.w = g.w;
-    dx[(2 * gq) * TC4 + tc] = lo;
-    dx[(2 * gq + 1) * TC4 + tc] = hi;
+    st_act4(dx, 4 * ((2 * gq) * TC4 + tc), lo, bf_out);
+    st_act4(dx, 4 * ((2 * gq + 1) * TC4 + tc), hi, bf_out);
   }
 }
 
@@ -498,40 +502,42 @@ static int ew_blocks(long long total) {
 }
 
 extern "C" int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int pool, float* y,
-                               uint8_t* idx, const int* seq_len, double* out_stats, void* stream) {
+                               uint8_t* idx, const int* seq_len, double* out_stats, int in_dtype, int out_dtype,
+                               void* stream) {
   if (!x || !y || pool < 1 || pool > 255 || F / pool < 1) return PBSED_EINVAL;
   const long long total = (long long)B * (F / pool) * T * C;
   if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)idx)) & 15) == 0) {
     const bool fused = out_stats && C <= 1024 && (256 % (C / 4)) == 0;
     if (fused)
       maxpool2_f4_kernel<true><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
-          reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
-          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, seq_len, out_stats);
+          x, F / 2, (long long)T * C / 4, y,
+          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, seq_len, out_stats, in_dtype, out_dtype);
     else
       maxpool2_f4_kernel<false><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
-          reinterpret_cast<const float4*>(x), F / 2, (long long)T * C / 4, reinterpret_cast<float4*>(y),
-          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, nullptr, nullptr);
+          x, F / 2, (long long)T * C / 4, y,
+          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, nullptr, nullptr, in_dtype, out_dtype);
     int rc = pbsed_after_launch();
     if (rc || fused || !out_stats) return rc;
-    return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, stream);
+    return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, out_dtype, stream);
   }
+  if (in_dtype != PBSED_F32 || out_dtype != PBSED_F32) return PBSED_EINVAL;
   maxpool_f_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, F, (long long)T * C, pool, y, idx, total);
   int rc = pbsed_after_launch();
   if (rc || !out_stats) return rc;
-  return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, stream);
+  return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, PBSED_F32, stream);
 }
 
 extern "C" int pbsed_maxpool_f_bwd(const float* dy, const uint8_t* idx, int B, int F, int T, int C,
-                                   int pool, float* dx, void* stream) {
+                                   int pool, float* dx, int in_dtype, int out_dtype, void* stream) {
   if (!dy || !idx || !dx || pool < 1 || F / pool < 1) return PBSED_EINVAL;
   const long long total = (long long)B * F * T * C;
   if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)dx) | ((uintptr_t)dy) | ((uintptr_t)idx)) & 15) == 0) {
     const long long total4_out = total / 8;
     maxpool2_f4_bwd_kernel<<<ew_blocks(total4_out), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(dy), reinterpret_cast<const uchar4*>(idx), (long long)T * C / 4,
-        reinterpret_cast<float4*>(dx), total4_out);
+        dy, reinterpret_cast<const uchar4*>(idx), (long long)T * C / 4, dx, total4_out, in_dtype, out_dtype);
     return pbsed_after_launch();
   }
+  if (in_dtype != PBSED_F32 || out_dtype != PBSED_F32) return PBSED_EINVAL;
   maxpool_f_bwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dy, idx, F, (long long)T * C, pool, dx, total);
   return pbsed_after_launch();
 }

@@ -266,6 +266,12 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
   cudaStream_t st = (cudaStream_t)stream;
   const int* load_seq = d->no_input_mask ? nullptr : seq_len;
   int fw_done = 0;
+  {                                 // first layer (one input channel): direct kernel, may write a bf16 map
+    int handled = 0;
+    rc = conv_cin1_fwd_dispatch(d, in, scale, shift, load_seq, W, bias, out, ep_src, st, &handled);
+    if (rc) return rc;
+    if (handled) goto sums;
+  }
   if (d->precision != 0) {
     // narrow 3x3 layers: the frequency-walking persistent kernel
     rc = tapgemm_fw_dispatch(d, in, scale, shift, seq_len, W, bias, out, ep_src, ep_scale, ep_shift,
@@ -278,15 +284,17 @@ extern "C" int pbsed_tapgemm(const pbsed_tapgemm_desc* d, const float* in, const
       if (handled || rc) return rc;
     }
   }
+  if (d->in_dtype != PBSED_F32 || d->out_dtype != PBSED_F32) return PBSED_EINVAL;   // bf16 maps: tensor-core kernels only
   rc = tapgemm_plain(d, p, in, scale, shift, load_seq, seq_len, W, bias, out, ep_src, ep_scale, ep_shift, st);
   if (rc) return rc;
+sums:
   // kernels without fused reductions: run them as separate passes over the finished map
   if (out_stats) {
-    rc = pbsed_channel_stats(out, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, out_stats, stream);
+    rc = pbsed_channel_stats(out, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, out_stats, d->out_dtype, stream);
     if (rc) return rc;
   }
   if (ep_sums)
-    rc = pbsed_norm_bwd_reduce(out, ep_src, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, ep_mean, ep_rstd, ep_sums, stream);
+    rc = pbsed_norm_bwd_reduce(out, ep_src, p.B, p.F_out, p.T, p.Cout, p.per_f, seq_len, ep_mean, ep_rstd, ep_sums, PBSED_F32, stream);
   return rc;
 }
 
@@ -441,6 +449,7 @@ extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in,
     rc = tapgemm_wgrad_tc_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
     if (handled || rc) return rc;
   }
+  if (d->in_dtype != PBSED_F32 || d->out_dtype != PBSED_F32) return PBSED_EINVAL;   // bf16 maps: tensor-core / narrow kernels only
   if (p.Cout <= 16 && p.Cin <= 16)
     return launch_wgrad<16, 16, 2, 2, 32>(p, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st);
   if (p.Cout <= 32 || p.Cin <= 32)

@@ -43,8 +43,9 @@ struct FwParams {
   int nkb, R;                 // channel blocks of 16; output rows per item (= 256 / Cout)
   int t_tiles, f_chunks, items;
   unsigned w_bytes;
+  int in_bf16, out_bf16;      // storage of `in` / of `out` and `ep_src` (bf16 activation maps)
   int nraw;                   // raw ring depth
-  unsigned raw_stage;         // bytes of one raw strip: 130 frames x Cin floats
+  unsigned raw_stage;         // bytes of one raw strip: 130 frames x Cin elements (fp32 or bf16)
 };
 
 struct __align__(16) FwCtl {
@@ -144,7 +145,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
       const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
       for (int f = f_lo; f <= f_hi; ++f, ++sit) {
         const int rs = sit % p.nraw;
-        const float* raw = reinterpret_cast<const float*>(r_smem + rs * p.raw_stage);
+        const uint8_t* raw = r_smem + rs * p.raw_stage;
         mbar_wait(&ctl->raw_full[rs], (sit / p.nraw) & 1);             // the raw strip has landed
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -162,7 +163,9 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
             if (r >= FW_ROWS) break;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t >= 0 && t < len_in) {
-              x = *reinterpret_cast<const float4*>(raw + r * p.Cin + kb * FW_KB + c * 4);
+              const uint32_t e = (uint32_t)(r * p.Cin + kb * FW_KB + c * 4);
+              x = p.in_bf16 ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(raw + 2 * e))
+                            : *reinterpret_cast<const float4*>(raw + 4 * e);
               if (scale) {
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
@@ -217,9 +220,9 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
       const int nsteps = R * CH;
       float4 nxt[4];
       if (use_src && grp < nsteps) {
-        const float* sp = ep_src + (orow0 + (long long)(grp / CH) * p.T) * Cout + cc;
+        const long long sp = (orow0 + (long long)(grp / CH) * p.T) * Cout + cc;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(sp + 4 * q));
+        for (int q = 0; q < 4; ++q) nxt[q] = ld_act4(ep_src, sp + 4 * q, p.out_bf16);
       }
       for (int step = grp; step < nsteps; step += 2) {
         const int r = step / CH;
@@ -228,9 +231,9 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
 #pragma unroll
         for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
         if (use_src && step + 2 < nsteps) {
-          const float* sp = ep_src + (orow0 + (long long)((step + 2) / CH) * p.T) * Cout + cc;
+          const long long sp = (orow0 + (long long)((step + 2) / CH) * p.T) * Cout + cc;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) nxt[q] = __ldg(reinterpret_cast<const float4*>(sp + 4 * q));
+          for (int q = 0; q < 4; ++q) nxt[q] = ld_act4(ep_src, sp + 4 * q, p.out_bf16);
         }
         mbar_wait(&ctl->acc_full[h][r], (li >> 1) & 1);
         tc_fence_after();
@@ -256,7 +259,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
               o.x = sv.x > 0.f ? o.x : 0.f; o.y = sv.y > 0.f ? o.y : 0.f;
               o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
             }
-            *reinterpret_cast<float4*>(out + obase + j) = o;
+            st_act4(out, obase + j, o, p.out_bf16);
             if (want_sums && valid) {
               float4 w2 = o;                           // out_stats: sum, sum of squares
               if (!out_stats) {                        // ep_sums: sum g, sum g * xhat
@@ -350,13 +353,15 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
         const int fo0 = fc * R, t0 = tt * FW_TM;
         const int f_lo = max(fo0 - 1, 0), f_hi = min(fo0 + R, p.F - 1);
         const int ta = max(t0 - 1, 0), tb = min(t0 + FW_TM, p.T - 1);
-        const uint32_t bytes = (uint32_t)(tb - ta + 1) * p.Cin * 4;
+        const uint32_t esz = p.in_bf16 ? 2u : 4u;
+        const uint32_t bytes = (uint32_t)(tb - ta + 1) * p.Cin * esz;
         for (int f = f_lo; f <= f_hi; ++f, ++sit) {
           const int rs = sit % p.nraw;
           mbar_wait(&ctl->raw_empty[rs], ((sit / p.nraw) & 1) ^ 1);
           mbar_expect_tx(&ctl->raw_full[rs], bytes);
-          bulk_g2s(r_smem + rs * p.raw_stage + (uint32_t)(ta - (t0 - 1)) * p.Cin * 4,
-                   in + (((long long)b * p.F + f) * p.T + ta) * p.Cin, bytes, &ctl->raw_full[rs]);
+          bulk_g2s(r_smem + rs * p.raw_stage + (uint32_t)(ta - (t0 - 1)) * p.Cin * esz,
+                   reinterpret_cast<const uint8_t*>(in) + (((long long)b * p.F + f) * p.T + ta) * p.Cin * esz, bytes,
+                   &ctl->raw_full[rs]);
         }
       }
     }
@@ -421,7 +426,8 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)scale | (uintptr_t)shift |
         (uintptr_t)ep_src | (uintptr_t)ep_scale | (uintptr_t)ep_shift | (uintptr_t)ep_mean | (uintptr_t)ep_rstd) & 15) != 0)
     return 0;
-  p.raw_stage = (unsigned)FW_ROWS * p.Cin * 4;
+  p.in_bf16 = d->in_dtype == PBSED_BF16; p.out_bf16 = d->out_dtype == PBSED_BF16;
+  p.raw_stage = (unsigned)FW_ROWS * p.Cin * 4;                    // sized for fp32; bf16 strips use half of it
   p.nraw = FW_NRAW * FW_KB / p.Cin;
   float* img = reinterpret_cast<float*>(workspace);
   fwprep_kernel<<<cdiv(p.w_bytes / 8, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,

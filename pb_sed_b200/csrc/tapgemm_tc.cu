@@ -100,17 +100,20 @@ struct __align__(16) SmemCtl {
 
 // FW_PROD producer / epilogue threads (4 or 8 warps), then one MMA warp and one weight-loader warp.
 // 8 warps feed the big tiles faster; 4 keep more CTAs co-resident for the narrow, latency-bound layers.
-template <int MT, int NBUF, int FW_PROD>
+// IO: bit 0 = `in` is a bf16 map, bit 1 = `out` and `ep_src` are bf16 maps (compile-time, so the fp32
+// instantiations keep their register budget)
+template <int MT, int NBUF, int FW_PROD, int IO>
 __global__ void __launch_bounds__(FW_PROD + 64, FW_PROD == 128 ? 4 : (MT <= 2 ? 2 : 1))   // MT <= 2: two CTAs per SM must stay resident (<= 96 registers)
-tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restrict__ scale,
+tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
                   const float* __restrict__ img, const float* __restrict__ bias,
-                  float* __restrict__ out, const float* __restrict__ ep_src,
+                  void* __restrict__ out, const void* __restrict__ ep_src,
                   const float* __restrict__ ep_scale, const float* __restrict__ ep_shift,
                   double* __restrict__ out_stats, const float* __restrict__ ep_mean,
                   const float* __restrict__ ep_rstd, double* __restrict__ ep_sums,
                   const int* __restrict__ load_seq_len, int t_super, int ctl_pad, int stat_n) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int IN_BF = IO & 1, OUT_BF = (IO >> 1) & 1;
   const int N = p.N;
   constexpr int RMAX = MT * TILE_M + 2 * HALO;         // strip rows
   constexpr uint32_t A_PART = KCH * RMAX * 16;         // bytes of one hi (or lo) strip stage
@@ -169,7 +172,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
     };
     auto issue = [&]() {
       const int f_src = fo + p.g_df[g];
-      const float* src = in + ((long long)b * p.F_in + f_src) * p.T * p.in_stride + kb * KB + c * 4;
+      const long long src = ((long long)b * p.F_in + f_src) * p.T * p.in_stride + kb * KB + c * 4;
       if (scale) {
         const int aff = (p.per_f ? f_src * p.Cin : 0) + kb * KB + c * 4;
         sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
@@ -180,7 +183,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         const int r = r0 + RSTEP * u, t = t0 + r - HALO;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < nrows && t >= 0 && t < len_in)
-          v[u] = __ldg(reinterpret_cast<const float4*>(src + (long long)t * p.in_stride));
+          v[u] = ld_act4(in, src + (long long)t * p.in_stride, IN_BF);
       }
     };
     bool have = advance();
@@ -247,9 +250,15 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
           const int r = idx / nq, q = idx - r * nq;
           const bool ok = tbase + r < len_b;
-          const float* src = ep_src + (orow0 + (ok ? tbase + r : t0)) * p.out_stride + n0 + 4 * q;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                       ::"r"(smem_u32(tile2 + r * LDT + 4 * q)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+          const long long se = (orow0 + (ok ? tbase + r : t0)) * p.out_stride + n0 + 4 * q;
+          if (OUT_BF)      // a bf16 quad lands in the first 8 bytes of the fp32 quad's slot, converted when read back
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+                         ::"r"(smem_u32(tile2 + r * LDT + 4 * q)), "l"(reinterpret_cast<const __nv_bfloat16*>(ep_src) + se),
+                           "r"(ok ? 8 : 0) : "memory");
+          else
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                         ::"r"(smem_u32(tile2 + r * LDT + 4 * q)), "l"(reinterpret_cast<const float*>(ep_src) + se),
+                           "r"(ok ? 16 : 0) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
@@ -274,7 +283,8 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
           const int r = idx / nq, q = idx - r * nq;
           float4 o = *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
-          const float4 x = *reinterpret_cast<const float4*>(tile2 + r * LDT + 4 * q);
+          const float4 x = OUT_BF ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(tile2 + r * LDT + 4 * q))
+                                  : *reinterpret_cast<const float4*>(tile2 + r * LDT + 4 * q);
           float4 sv = x;
           if (tbase + r >= len_b) sv = make_float4(0.f, 0.f, 0.f, 0.f);
           else if (ep_scale) {
@@ -285,8 +295,7 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
           }
           o.x = sv.x > 0.f ? o.x : 0.f; o.y = sv.y > 0.f ? o.y : 0.f;
           o.z = sv.z > 0.f ? o.z : 0.f; o.w = sv.w > 0.f ? o.w : 0.f;
-          if (tbase + r < p.T)
-            *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) = o;
+          if (tbase + r < p.T) st_act4(out, (orow0 + tbase + r) * p.out_stride + n0 + 4 * q, o, OUT_BF);
           if (ep_sums || out_stats) *reinterpret_cast<float4*>(tile + r * LDT + 4 * q) = o;
           if (ep_sums) {
             const float4 mu = __ldg(reinterpret_cast<const float4*>(ep_mean + ep_base + 4 * q));
@@ -301,8 +310,8 @@ tapgemm_tc_kernel(TcParams p, const float* __restrict__ in, const float* __restr
         for (int idx = tid; idx < TILE_M * nq; idx += FW_PROD) {
           const int r = idx / nq, q = idx - r * nq;
           if (tbase + r < p.T)
-            *reinterpret_cast<float4*>(out + (orow0 + tbase + r) * p.out_stride + n0 + 4 * q) =
-                *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q);
+            st_act4(out, (orow0 + tbase + r) * p.out_stride + n0 + 4 * q,
+                    *reinterpret_cast<const float4*>(tile + r * LDT + 4 * q), OUT_BF);
         }
       }
       if (out_stats || ep_sums) {
@@ -433,6 +442,7 @@ struct WgParams {
   int g_df[MAXG], g_n[MAXG], g_tap[MAXG][3], g_dt[MAXG][3];
   int row_splits;
   int single;            // 1: one TF32 pass (precision 3)
+  int in_bf16, out_bf16; // storage of `in` / `dout` (bf16 activation maps; wgrad_tma_kernel only)
 };
 
 struct __align__(16) WgCtl {
@@ -754,7 +764,7 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
   const uint32_t Z_LBO = 128 * 16, A_LBO = (uint32_t)p.Nc * 16;
   const uint32_t Z_PART = WG_ZCH * Z_LBO, A_PART = WG_ACH * A_LBO;
   const uint32_t STAGE = 2 * Z_PART + 2 * A_PART;
-  const uint32_t RAW_Z = WG_KR * (uint32_t)p.Ms * 4, RAW_A = WG_RAW_AROWS * (uint32_t)p.Nc * 4;
+  const uint32_t RAW_Z = WG_KR * (uint32_t)p.Ms * (p.out_bf16 ? 2u : 4u), RAW_A = WG_RAW_AROWS * (uint32_t)p.Nc * (p.in_bf16 ? 2u : 4u);
   const uint32_t RAW = RAW_Z + RAW_A;
   uint8_t* raw_base = smem_raw + WG_STAGES * STAGE;
   WgTmaCtl* ctl = reinterpret_cast<WgTmaCtl*>(raw_base + (uint32_t)raw_stages * RAW);
@@ -808,14 +818,14 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       const int len_out = p.mask_out ? len_b : p.T;
       const int t_end = min(p.T, (tb + 1) * WG_TB);
       if (!f_ok) {                                 // bias-only visit of a border row group: plain loads
-        const float* zsrc = dout + ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
+        const long long zsrc = ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
         for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR)
           for (int j = zj0; j < WG_ZCH; j += zjs)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int t = t0 + j + 8 * i;
               if (t < len_out) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(zsrc + (long long)t * p.out_stride));
+                const float4 v = ld_act4(dout, zsrc + (long long)t * p.out_stride, p.out_bf16);
                 bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
               }
             }
@@ -828,8 +838,8 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       }
       for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
         const int rs = it % raw_stages, slot = it % WG_STAGES;
-        const float* rz = reinterpret_cast<const float*>(raw_base + (uint32_t)rs * RAW);
-        const float* ra = reinterpret_cast<const float*>(raw_base + (uint32_t)rs * RAW + RAW_Z);
+        const uint8_t* rz = raw_base + (uint32_t)rs * RAW;
+        const uint8_t* ra = rz + RAW_Z;
         uint8_t* z_hi = smem_raw + slot * STAGE;
         uint8_t* z_lo = z_hi + Z_PART;
         uint8_t* a_hi = z_lo + Z_PART;
@@ -841,8 +851,11 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = j + 8 * i;
-            v[i] = (t0 + r < len_out) ? *reinterpret_cast<const float4*>(rz + r * p.Ms + zqi * 4)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t e = (uint32_t)(r * p.Ms + zqi * 4);
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + r < len_out)
+              v[i] = p.out_bf16 ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(rz + 2 * e))
+                                : *reinterpret_cast<const float4*>(rz + 4 * e);
           }
           const uint32_t o = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
           split_store(z_hi, z_lo, o + 0 * zq * 16, v[0].x, v[1].x, v[2].x, v[3].x, p.single);
@@ -861,7 +874,9 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
             const int r = jj + 8 * i, t = t0 + r - 1;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (t >= 0 && t < len_b) {
-              x = *reinterpret_cast<const float4*>(ra + r * p.Nc + aqi * 4);
+              const uint32_t e = (uint32_t)(r * p.Nc + aqi * 4);
+              x = p.in_bf16 ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(ra + 2 * e))
+                            : *reinterpret_cast<const float4*>(ra + 4 * e);
               if (scale) {
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
@@ -1068,17 +1083,26 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   dim3 grid(t_super * p.n_slices, p.F_out, p.B);
   if (grid.y > 65535 || grid.z > 65535) return 0;
   cudaError_t e;
-#define PBSED_TC_LAUNCH(MTV, NBV, PRV)                                                                \
-  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV, NBV, PRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  const int io = (d->in_dtype == PBSED_BF16 ? 1 : 0) | (d->out_dtype == PBSED_BF16 ? 2 : 0);
+#define PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, IOV)                                                        \
+  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV, NBV, PRV, IOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                 \
-  tapgemm_tc_kernel<MTV, NBV, PRV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
+  tapgemm_tc_kernel<MTV, NBV, PRV, IOV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
                                                   ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
                                                   d->no_input_mask ? nullptr : seq_len, t_super, (int)pad, stat_n);
+#define PBSED_TC_LAUNCH(MTV, NBV, PRV)                                                                \
+  switch (io) {                                                                                       \
+    case 0: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 0) } break;                                           \
+    case 1: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 1) } break;                                           \
+    case 2: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 2) } break;                                           \
+    default: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 3) } break;                                          \
+  }
   pbsed_note_kernel(nbuf == 2 ? "tapgemm_tc_kernel<2,2,256>" : mt == 4 ? "tapgemm_tc_kernel<4,4,256>" : mt == 2 ? "tapgemm_tc_kernel<2,4,256>"
                     : p.N <= 32 ? "tapgemm_tc_kernel<1,4,128>" : "tapgemm_tc_kernel<1,4,256>");
   if (nbuf == 2) { PBSED_TC_LAUNCH(2, 2, 256) } else if (mt == 4) { PBSED_TC_LAUNCH(4, 4, 256) } else if (mt == 2) { PBSED_TC_LAUNCH(2, 4, 256) }
   else if (p.N <= 32) { PBSED_TC_LAUNCH(1, 4, 128) } else { PBSED_TC_LAUNCH(1, 4, 256) }
 #undef PBSED_TC_LAUNCH
+#undef PBSED_TC_LAUNCH_IO
   *handled = 1;
   int rc = pbsed_after_launch();
   if (rc || !want_sums) return rc;
@@ -1105,6 +1129,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
   p.w_tap_stride = d->w_tap_stride; p.w_sn = d->w_sn; p.w_sc = d->w_sc;
   p.single = d->precision == 3;
+  p.in_bf16 = d->in_dtype == PBSED_BF16; p.out_bf16 = d->out_dtype == PBSED_BF16;
   p.Ms = d->Cout < NSLICE ? d->Cout : NSLICE;
   p.m_slices = d->Cout / p.Ms;
   p.Nc = d->Cin < NSLICE ? d->Cin : NSLICE;
@@ -1125,14 +1150,14 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   static const int use_tma = getenv("PBSED_WG_TMA") ? atoi(getenv("PBSED_WG_TMA")) : 1;
   const long long rows_z = (long long)p.B * p.F_out * p.T, rows_a = (long long)p.B * p.F_in * p.T;
   if (use_tma && rows_z < (1LL << 31) && rows_a < (1LL << 31)) {
-    const size_t raw = (size_t)WG_KR * p.Ms * 4 + (size_t)WG_RAW_AROWS * p.Nc * 4;
+    const size_t raw = (size_t)WG_KR * p.Ms * (p.out_bf16 ? 2 : 4) + (size_t)WG_RAW_AROWS * p.Nc * (p.in_bf16 ? 2 : 4);
     const size_t budget = 227 * 1024 - WG_STAGES * stage - sizeof(WgTmaCtl) - 256;
     int raw_stages = (int)(budget / raw);
     if (raw_stages > WG_RAW_MAX) raw_stages = WG_RAW_MAX;
     CUtensorMap tm_z, tm_a;
     if (raw_stages >= 2 &&
-        make_tmap_2d(&tm_z, dout, p.Cout, rows_z, p.out_stride, p.Ms, WG_KR) &&
-        make_tmap_2d(&tm_a, in, p.Cin, rows_a, p.in_stride, p.Nc, WG_RAW_AROWS)) {
+        make_tmap_2d(&tm_z, dout, p.Cout, rows_z, p.out_stride, p.Ms, WG_KR, p.out_bf16) &&
+        make_tmap_2d(&tm_a, in, p.Cin, rows_a, p.in_stride, p.Nc, WG_RAW_AROWS, p.in_bf16)) {
       int rs = 148 / roles;                            // one CTA per SM: a single wave, deep prefetch instead of co-residency
       if (rs > units) rs = units;
       if (rs < 1) rs = 1;
@@ -1147,6 +1172,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
       return pbsed_after_launch();
     }
   }
+  if (p.in_bf16 || p.out_bf16) return PBSED_EINVAL;    // bf16 maps need the TMA-fed kernel
   int rs = (2 * 148) / roles;                       // <= 2 CTAs per SM's worth, never a ragged extra wave
   if (rs >= 8 * 2 && units / rs < 4) rs = 148 / roles;
   // 128-wide input slices need 147 KB of shared memory: ONE CTA per SM, so 2 x 148 CTAs would run as two

@@ -132,16 +132,18 @@ static PbsedEncodeTiled tmap_encoder() {
   }
   return fn;
 }
-// fp32 matrix [rows][cols] with a row pitch of `stride` floats; box = box_rows x box_cols, no swizzle, zero fill
-static bool make_tmap_2d(CUtensorMap* tm, const float* base, int cols, long long rows, long long stride,
-                         int box_cols, int box_rows) {
+// fp32 (or bf16) matrix [rows][cols] with a row pitch of `stride` ELEMENTS; box = box_rows x box_cols, no swizzle,
+// zero fill
+static bool make_tmap_2d(CUtensorMap* tm, const void* base, int cols, long long rows, long long stride,
+                         int box_cols, int box_rows, int bf16 = 0) {
   PbsedEncodeTiled enc = tmap_encoder();
   if (!enc) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(float)};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * (bf16 ? 2 : 4)};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  return enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+             strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

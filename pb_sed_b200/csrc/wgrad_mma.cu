@@ -18,6 +18,7 @@ namespace {
 struct WmParams {
   int B, F, T, relu, mask_out, single;
   int in_stride, out_stride;
+  int in_bf16, out_bf16;      // storage type of `in` / `dout` (bf16 activation maps)
   long long w_tap_stride, w_sn, w_sc;
 };
 
@@ -73,12 +74,12 @@ wgrad_mma_kernel(WmParams p, const float* __restrict__ in, const float* __restri
     const int len_out = p.mask_out ? len_b : p.T;
     __syncthreads();                                   // previous unit's readers are done
     {   // dout tile (+ bias partial sums: tid % ZQ is loop invariant)
-      const float* z = dout + ((long long)b * p.F + f) * p.T * p.out_stride;
+      const long long z0 = ((long long)b * p.F + f) * p.T * p.out_stride;
       for (int i = tid; i < TT * ZQ; i += 256) {
         const int r = i / ZQ, q = i % ZQ;
         const int t = t0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < len_out) v = __ldg(reinterpret_cast<const float4*>(z + (long long)t * p.out_stride + q * 4));
+        if (t < len_out) v = ld_act4(dout, z0 + (long long)t * p.out_stride + q * 4, p.out_bf16);
         *reinterpret_cast<float4*>(zs + r * LDZ + q * 4) = v;
         bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
       }
@@ -87,13 +88,13 @@ wgrad_mma_kernel(WmParams p, const float* __restrict__ in, const float* __restri
     for (int d = 0; d < 3; ++d) {   // input strips f-1, f, f+1, frames t0-1 .. t0+TT
       const int fs = f + d - 1;
       const bool f_ok = fs >= 0 && fs < p.F;
-      const float* a = in + ((long long)b * p.F + (f_ok ? fs : 0)) * p.T * p.in_stride;
+      const long long a0 = ((long long)b * p.F + (f_ok ? fs : 0)) * p.T * p.in_stride;
       for (int i = tid; i < (TT + 2) * (CIN / 4); i += 256) {
         const int r = i / (CIN / 4), q = i % (CIN / 4);
         const int t = t0 + r - 1;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f_ok && t >= 0 && t < len_b) {
-          v = __ldg(reinterpret_cast<const float4*>(a + (long long)t * p.in_stride + q * 4));
+          v = ld_act4(in, a0 + (long long)t * p.in_stride + q * 4, p.in_bf16);
           if (scale) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + q * 4));
             const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + q * 4));
@@ -202,6 +203,7 @@ int wgrad_mma_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float
   p.B = d->B; p.F = d->F_in; p.T = d->T; p.relu = d->relu; p.mask_out = mask_out;
   p.single = d->precision == 3;
   p.in_stride = d->in_stride > 0 ? d->in_stride : d->Cin;
+  p.in_bf16 = d->in_dtype == PBSED_BF16; p.out_bf16 = d->out_dtype == PBSED_BF16;
   p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
   p.w_tap_stride = d->w_tap_stride; p.w_sn = d->w_sn; p.w_sc = d->w_sc;
   if (p.in_stride % 4 || p.out_stride % 4) return 0;

@@ -129,10 +129,11 @@ class CRNN(base.SoundEventModel):
             weak = targets[0]
             wm = (weak < .01) | (weak > .99)
             review['scalars']['weak_label_rate'] = wm.float().mean().item()
-            if self.strong_fwd_bwd_loss_weight > 0. and not self.slat:
-                bt = targets[1]
+            if self.strong_fwd_bwd_loss_weight > 0.:
+                wt = weak * wm
+                bt = wt[..., None].expand(y_fwd.shape) if self.slat else targets[1]      # crnn.py:130-134
                 bm = ((bt > .99) | (bt < .01))
-                bm = bm * (bm.float().mean(-1, keepdim=True) > .999) * ((weak * wm) > .99)[..., None]
+                bm = bm * (bm.float().mean(-1, keepdim=True) > .999) * (wt > .99)[..., None]
                 review['scalars']['boundary_label_rate'] = bm.float().mean().item()
             else:
                 review['scalars']['boundary_label_rate'] = 0.

@@ -357,8 +357,17 @@ class _CNN(nn.Module):
             return self.norms[i]
         return self.norms[i - 1] if i > 0 else None
 
-    def forward_native(self, x, seq, stats_in=None, next_stats=None):
+    @staticmethod
+    def _bf16_ok(conv):
+        """can this layer read AND write bf16 activation maps?  (the tensor-core / narrow kernels: channel counts
+        that are multiples of 16, a tap table the kernels hold)"""
+        return conv.in_channels % 16 == 0 and conv.out_channels % 16 == 0 and len(conv.taps) <= ops._lib.MAX_TAPS
+
+    def forward_native(self, x, seq, stats_in=None, next_stats=None, act_dtype=torch.float32, last_act_dtype=torch.float32):
         """x (B,F,T,C) native -> (B,F',T,C').
+
+        act_dtype: storage type of the maps BETWEEN the layers (``ops.act_dtype()``: bf16 in the 'bf16' mode; a
+        layer writes bf16 only if it and its consumer have kernels for it); last_act_dtype: of the stack's output.
 
         stats_in: batch statistics of x already produced by the previous stack's last conv.
         next_stats: None, or 'c' / 'fc' -- also return the statistics of the output (per channel /
@@ -402,7 +411,16 @@ class _CNN(nn.Module):
             live = self.training and not (norm is not None and norm.frozen_stats)
             if stats is not None and not live:
                 stats = None
-            cfg = dict(F_in=F_in, F_out=1 if fh > 1 else F_in, taps=taps, relu=relu,
+            out_dtype = torch.float32
+            if act_dtype == torch.bfloat16:
+                writes = self._bf16_ok(conv) or (conv.in_channels == 1 and conv.out_channels in (16, 32))
+                if i + 1 < n:
+                    out_dtype = torch.bfloat16 if (writes and self._bf16_ok(self.convs[i + 1].conv)) else torch.float32
+                else:
+                    out_dtype = last_act_dtype if writes else torch.float32
+            if x.dtype == torch.bfloat16 and not self._bf16_ok(conv):
+                x = x.float()                   # a layer without bf16 kernels (odd channel counts): widen its input
+            cfg = dict(out_dtype=out_dtype, F_in=F_in, F_out=1 if fh > 1 else F_in, taps=taps, relu=relu,
                        per_f=fh > 1, pool=self._pool(self.pool_sizes[i]), norm=norm is not None,
                        eps=norm.eps if norm is not None else 0.,
                        momentum=norm.momentum if norm is not None else 0.,
@@ -482,11 +500,15 @@ class CNN(nn.Module):
         # the last cnn_2d conv's epilogue
         n0 = self.cnn_1d._input_norm(0)
         want = 'fc' if (self.training and n0 is not None and not n0.frozen_stats) else None
+        # 'bf16' mode: the maps between the conv layers (and their gradients) live in HBM as bf16; the stack's
+        # output (the GRU input) is fp32
+        adt = ops.act_dtype()
+        mid = adt if (adt == torch.bfloat16 and _CNN._bf16_ok(self.cnn_1d.convs[0].conv)) else torch.float32
         if want:
-            x, stats = self.cnn_2d.forward_native(x, seq, next_stats=want)
+            x, stats = self.cnn_2d.forward_native(x, seq, next_stats=want, act_dtype=adt, last_act_dtype=mid)
         else:
-            x, stats = self.cnn_2d.forward_native(x, seq), None
-        x = self.cnn_1d.forward_native(x, seq, stats_in=stats)            # (B,1,T,D)
+            x, stats = self.cnn_2d.forward_native(x, seq, act_dtype=adt, last_act_dtype=mid), None
+        x = self.cnn_1d.forward_native(x, seq, stats_in=stats, act_dtype=adt)            # (B,1,T,D) fp32
         return x.squeeze(1)
 
     def forward(self, x, seq_len=None, condition=None):

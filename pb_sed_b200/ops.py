@@ -19,8 +19,13 @@ from ._lib import TapGemmDesc, call
 
 import os
 
-PRECISION = {'fp32': 0, 'tf32x3': 1, 'tf32': 3}
+PRECISION = {'fp32': 0, 'tf32x3': 1, 'tf32': 3, 'bf16': 3}
 _default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'tf32x3')]
+# storage type of the conv-stack activation maps and their gradients in HBM: torch.float32, or torch.bfloat16 in
+# the 'bf16' mode (BASELINE configs[2] / [4]).  In that mode the conv stacks run ONE tensor-core pass: bf16
+# activations (exact in the kind::tf32 operand format) times TF32-rounded weights, fp32 accumulation; master weights,
+# batch statistics, the GRU and the optimizer stay fp32.
+_act_dtype = torch.bfloat16 if os.environ.get('PBSED_PRECISION') == 'bf16' else torch.float32
 
 
 def set_default_precision(p):
@@ -28,8 +33,27 @@ def set_default_precision(p):
     fp32-equivalent, the default) or 'tf32' (tcgen05, ONE TF32 pass with fp32 accumulation: the
     reduced-precision mode offered for the BASELINE "bf16" configurations -- 10 mantissa bits, i.e.
     at least bf16's 7, at a third of the tensor work)."""
-    global _default_precision
+    global _default_precision, _act_dtype
     _default_precision = PRECISION[p] if isinstance(p, str) else int(p)
+    _act_dtype = torch.bfloat16 if p == 'bf16' else torch.float32
+
+
+def act_dtype():
+    """storage dtype of conv-stack activation maps (torch.bfloat16 in the 'bf16' mode)."""
+    return _act_dtype
+
+
+def _dt(t):
+    """C-ABI dtype code of an activation tensor / torch dtype: 0 = fp32, 1 = bf16."""
+    d = t if isinstance(t, torch.dtype) else t.dtype
+    return 1 if d == torch.bfloat16 else 0
+
+
+def _actc(t):
+    """contiguous activation map in one of the two storage types."""
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        t = t.float()
+    return t.contiguous()
 
 
 # ------------------------------------------------------------------ weight-gradient side stream
@@ -202,7 +226,7 @@ def from_native(x):
 
 # ------------------------------------------------------------------ raw kernels
 def make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=False, per_f=False, transpose_w=False,
-              in_stride=0, out_stride=0, precision=None, no_input_mask=False):
+              in_stride=0, out_stride=0, precision=None, no_input_mask=False, in_dtype=0, out_dtype=0):
     d = TapGemmDesc()
     d.B, d.F_in, d.F_out, d.T, d.Cin, d.Cout = B, F_in, F_out, T, Cin, Cout
     d.ntaps = len(taps)
@@ -218,6 +242,7 @@ def make_desc(B, F_in, F_out, T, Cin, Cout, taps, relu=False, per_f=False, trans
     d.in_stride, d.out_stride = in_stride, out_stride
     d.precision = _default_precision if precision is None else precision
     d.no_input_mask = int(no_input_mask)
+    d.in_dtype, d.out_dtype = int(in_dtype), int(out_dtype)
     return d
 
 
@@ -225,7 +250,8 @@ def tapgemm(x, W, bias, desc, scale=None, shift=None, seq=None, ep_src=None, ep_
             ep_shift=None, out=None, x_ptr=None, out_stats=None, ep_mean=None, ep_rstd=None, ep_sums=None):
     rows = desc.B * desc.F_out * desc.T
     if out is None:
-        out = torch.empty((rows, desc.Cout), device=W.device, dtype=torch.float32)
+        out = torch.empty((rows, desc.Cout), device=W.device,
+                          dtype=torch.bfloat16 if desc.out_dtype == 1 else torch.float32)
     ws, ws_bytes = None, 0
     if desc.precision != 0:
         ws_bytes = int(_lib.load().pbsed_tapgemm_workspace_bytes(ctypes.byref(desc)))
@@ -271,10 +297,11 @@ class ConvLayerFn(torch.autograd.Function):
         """returns (y, stats_out): stats_out = (Cout[*F_out], 2) float64 sum / sum-of-squares of y over
         valid frames when cfg['want_stats'] (fused into the conv epilogue), else an empty tensor.
         stats_in: the same quantity for x, produced by the previous layer (skips the statistics pass)."""
-        x = _f32c(x)
+        x = _actc(x)
         B, F_in, T, Cin = x.shape
         ntaps, Cout, Cin_w = weight.shape
         assert Cin_w == Cin and F_in == cfg['F_in'], (weight.shape, x.shape, cfg)
+        idt, odt = _dt(x), _dt(cfg.get('out_dtype', torch.float32))
         F_out, pool = cfg['F_out'], cfg.get('pool', 1)
         per_f = cfg.get('per_f', False)
         scale = shift = smean = srstd = None
@@ -289,7 +316,7 @@ class ConvLayerFn(torch.autograd.Function):
                 else:
                     stats = _stats_buffer(nch, x.device)
                     call('pbsed_channel_stats', _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                         _ptr(stats), _stream())
+                         _ptr(stats), idt, _stream())
                 smean = torch.empty(nch, device=x.device)
                 srstd = torch.empty(nch, device=x.device)
                 call('pbsed_norm_finalize', _ptr(stats), _sync_count_(stats, nch, count), nch, _ptr(gamma), _ptr(beta),
@@ -302,29 +329,29 @@ class ConvLayerFn(torch.autograd.Function):
         # the reference masks padded frames inside Normalization only: a bare conv (layer 0, whose
         # tag-condition channels are NOT zero at padded frames) reads its input unmasked
         desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
-                         no_input_mask=not cfg['norm'])
+                         no_input_mask=not cfg['norm'], in_dtype=idt, out_dtype=odt)
         stats_out = None
         if cfg.get('want_stats') and pool == 1:
             sp = cfg.get('stats_per_f', False)
             desc_s = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
-                               no_input_mask=not cfg['norm'])
+                               no_input_mask=not cfg['norm'], in_dtype=idt, out_dtype=odt)
             stats_out = _stats_buffer((F_out if sp else 1) * Cout, x.device)
             if sp == per_f:
                 z = tapgemm(x, weight, bias, desc_s, scale, shift, seq, out_stats=stats_out)
             else:      # statistics indexed differently from the load affine: separate pass
                 z = tapgemm(x, weight, bias, desc, scale, shift, seq)
-                call('pbsed_channel_stats', _ptr(z), B, F_out, T, Cout, int(sp), seq.ptr, _ptr(stats_out), _stream())
+                call('pbsed_channel_stats', _ptr(z), B, F_out, T, Cout, int(sp), seq.ptr, _ptr(stats_out), odt, _stream())
             z = z.view(B, F_out, T, Cout)
         else:
             z = tapgemm(x, weight, bias, desc, scale, shift, seq).view(B, F_out, T, Cout)
         idx = None
         if pool > 1:
-            y = torch.empty((B, F_out // pool, T, Cout), device=x.device)
+            y = torch.empty((B, F_out // pool, T, Cout), device=x.device, dtype=z.dtype)
             idx = torch.empty(y.shape, device=x.device, dtype=torch.uint8)
             if cfg.get('want_stats') and not cfg.get('stats_per_f', False):
                 stats_out = _stats_buffer(Cout, x.device)      # statistics of the pooled map, same pass
             call('pbsed_maxpool_f', _ptr(z), B, F_out, T, Cout, pool, _ptr(y), _ptr(idx), seq.ptr,
-                 _ptr(stats_out), _stream())
+                 _ptr(stats_out), odt, odt, _stream())
         else:
             y = z
         ctx.cfg, ctx.seq, ctx.count = cfg, seq, count
@@ -343,13 +370,17 @@ class ConvLayerFn(torch.autograd.Function):
         B, F_in, T, Cin = x.shape
         ntaps, Cout, _ = weight.shape
         F_out, pool, per_f = cfg['F_out'], cfg.get('pool', 1), cfg.get('per_f', False)
-        dy = _f32c(dy)
+        idt, odt = _dt(x), _dt(cfg.get('out_dtype', torch.float32))
+        dy = _actc(dy)
+        if _dt(dy) != odt:
+            dy = dy.to(torch.bfloat16 if odt else torch.float32)
         if pool > 1:
-            dz = torch.empty((B, F_out, T, Cout), device=x.device)
-            call('pbsed_maxpool_f_bwd', _ptr(dy), _ptr(idx), B, F_out, T, Cout, pool, _ptr(dz), _stream())
+            dz = torch.empty((B, F_out, T, Cout), device=x.device, dtype=dy.dtype)
+            call('pbsed_maxpool_f_bwd', _ptr(dy), _ptr(idx), B, F_out, T, Cout, pool, _ptr(dz), odt, odt, _stream())
         else:
             dz = dy
-        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f)
+        desc = make_desc(B, F_in, F_out, T, Cin, Cout, cfg['taps'], relu=cfg['relu'], per_f=per_f,
+                         in_dtype=idt, out_dtype=odt)
         dW, dW_ret = _grad_target(w_p)
         db, db_ret = _grad_target(b_p)
         if dW is not None:
@@ -361,7 +392,8 @@ class ConvLayerFn(torch.autograd.Function):
         norm_grads = cfg['norm'] and cfg['training'] and g_p is not None and g_p.requires_grad
         if ctx.needs_input_grad[0] or norm_grads:
             rtaps = [(-df, -dt) for df, dt in cfg['taps']]
-            ddesc = make_desc(B, F_out, F_in, T, Cout, Cin, rtaps, per_f=per_f, transpose_w=True)
+            ddesc = make_desc(B, F_out, F_in, T, Cout, Cin, rtaps, per_f=per_f, transpose_w=True,
+                              in_dtype=odt, out_dtype=idt)       # reads dz, writes g in the dtype of x (= ep_src)
             train_norm = cfg['norm'] and cfg['training']
             sums = None
             fuse = train_norm and cfg['relu']          # batch-norm backward pass 1 rides in the dgrad epilogue
@@ -377,7 +409,7 @@ class ConvLayerFn(torch.autograd.Function):
             if train_norm:
                 if not fuse:
                     call('pbsed_norm_bwd_reduce', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                         _ptr(smean), _ptr(srstd), _ptr(sums), _stream())
+                         _ptr(smean), _ptr(srstd), _ptr(sums), idt, _stream())
                 dga, dg_ret = _grad_target(g_p)
                 dbe, dbe_ret = _grad_target(be_p)
                 if _sync['on']:
@@ -386,19 +418,19 @@ class ConvLayerFn(torch.autograd.Function):
                     local = sums[:nch].float()
                     cnt = _sync_count_(sums, nch, ctx.count)
                     call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
-                         _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), cnt, _ptr(g), None, None, _stream())
+                         _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), cnt, _ptr(g), None, None, idt, _stream())
                     if dga is not None:
                         dga.add_(local[:, 1])
                         dbe.add_(local[:, 0])
                 else:
                     call('pbsed_norm_bwd_apply', _ptr(g), _ptr(x), B, F_in, T, Cin, int(per_f), seq.ptr,
                          _ptr(smean), _ptr(srstd), _ptr(gamma), _ptr(sums), ctx.count, _ptr(g),
-                         _ptr(dga), _ptr(dbe), _stream())
+                         _ptr(dga), _ptr(dbe), idt, _stream())
                 dx = g
             elif cfg['norm']:
                 # eval-mode norm is a fixed affine: dx = g * scale  (rare: frozen-stat finetuning)
                 sc = scale.view(F_in, 1, Cin) if per_f else scale
-                dx = g * sc
+                dx = (g * sc).to(g.dtype)
             else:
                 dx = g
             if not ctx.needs_input_grad[0]:

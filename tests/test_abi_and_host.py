@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert len(protos) >= 20
     for name in protos:
         assert hasattr(built_lib, name), name
-    assert built_lib.pbsed_abi_version() == 5
+    assert built_lib.pbsed_abi_version() == 6
     assert built_lib.pbsed_launch_count() >= 0
     assert isinstance(built_lib.pbsed_last_kernel(), bytes)      # const char* entry point (not an int prototype)
 

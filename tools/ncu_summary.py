@@ -99,5 +99,33 @@ def pipe(path):
               f'{gemm_p / gemm_t:.1f} %')
 
 
+def stalls(path, pattern='.', skip=0):
+    """source-level view of ONE launch of a --set full --import-source on capture: the most-sampled SASS
+    instructions and the stall-reason totals (python tools/ncu_summary.py stalls X.ncu-rep <kernel regex> <skip>)."""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--kernel-name', 'regex:' + pattern,
+                          '--launch-skip', str(skip), '--launch-count', '1'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3:
+        print('no source page')
+        return
+    print('## ' + rows[0][1][:120])
+    hdr, body = rows[1], rows[2:]
+    S, A = hdr.index('Source'), hdr.index('Warp Stall Sampling (All Samples)')
+    tot = sum(int(r[A]) for r in body if len(r) > A and r[A].isdigit())
+    reasons = {h: 0 for h in hdr if h.startswith('stall_') and 'Not Issued' not in h}
+    for r in body:
+        for h in reasons:
+            try:
+                reasons[h] += int(r[hdr.index(h)])
+            except (ValueError, IndexError):
+                pass
+    rt = max(sum(reasons.values()), 1)
+    print(f'   warp-state samples {tot}; by reason: ' +
+          ', '.join(f'{k[6:]} {100 * v / rt:.0f}%' for k, v in sorted(reasons.items(), key=lambda kv: -kv[1]) if v > .02 * rt))
+    top = sorted(((int(r[A]), i, r[S].strip()) for i, r in enumerate(body) if len(r) > A and r[A].isdigit()), reverse=True)[:14]
+    for n, i, src in top:
+        print(f'   {100 * n / max(tot, 1):5.1f}%  #{i:5d}  {src[:110]}')
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel, 'pipe': pipe}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'kernel': kernel, 'pipe': pipe, 'stalls': stalls}[sys.argv[1]](*sys.argv[2:])
