@@ -23,7 +23,7 @@ def _lib_loaded(built_lib):
 
 
 @pytest.mark.parametrize('B,F,T,Cin,Cout,taps', [
-    (4, 8, 500, 16, 16, TAPS_3x3),            # frequency-walking kernel
+    (4, 16, 500, 16, 16, TAPS_3x3),           # frequency-walking kernel
     (4, 8, 300, 32, 32, TAPS_3x3),
     (3, 4, 500, 64, 128, TAPS_3x3),           # generic tcgen05 kernel
     (2, 1, 500, 256, 256, [(0, -1), (0, 0), (0, 1)]),
