@@ -297,6 +297,7 @@ __device__ __forceinline__ NbaCoef nba_coef(const float4* __restrict__ mean, con
   return k;
 }
 
+template <int U>        // rows in flight per thread: 4 for fp32 maps, 8 for bf16 maps (same bytes in flight)
 __global__ void __launch_bounds__(256)
 norm_bwd_apply4_kernel(const void* __restrict__ g, const void* __restrict__ x, int F, int T, int C4,
                        int per_f, const int* __restrict__ seq_len, const float4* __restrict__ mean,
@@ -308,7 +309,6 @@ norm_bwd_apply4_kernel(const void* __restrict__ g, const void* __restrict__ x, i
   const long long stride = (long long)gridDim.x * blockDim.x;       // multiple of C4 (256 % C4 == 0)
   const int q = (int)(gtid % C4);
   const long long rstep = stride / C4, rows = total4 / C4;
-  constexpr int U = 4;
   int f_cur = -1;
   NbaCoef k;
   if (!per_f) k = nba_coef(mean, rstd, gamma, sums, inv_n, q);
@@ -369,11 +369,18 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
     const long long total4 = total / 4;
     int blocks4 = (int)((total4 + 255) / 256);
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;
-    norm_bwd_apply4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>(
-        g, x, F, T, C / 4, per_f, seq_len,
-        reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
-        reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
-        dgamma, dbeta, total4, nch, act_dtype);
+    if (act_dtype == PBSED_BF16)
+      norm_bwd_apply4_kernel<8><<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+          g, x, F, T, C / 4, per_f, seq_len,
+          reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
+          reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
+          dgamma, dbeta, total4, nch, 1);
+    else
+      norm_bwd_apply4_kernel<4><<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+          g, x, F, T, C / 4, per_f, seq_len,
+          reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
+          reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
+          dgamma, dbeta, total4, nch, 0);
     return pbsed_after_launch();
   }
   if (act_dtype != PBSED_F32) return PBSED_EINVAL;

@@ -13,3 +13,5 @@ try:
 except Exception as e:
     print('bench failed', e); print(open('gpurun_out/${TAG}_bench_bf16.err').read()[-1500:])
 PY
+timeout 600 python bench.py --workload audioset_stream --precision bf16 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_stream_bf16.json 2> gpurun_out/${TAG}_bench_stream_bf16.err; tail -c 400 gpurun_out/${TAG}_bench_stream_bf16.json; tail -c 600 gpurun_out/${TAG}_bench_stream_bf16.err
+timeout 600 python bench.py --global-batch 256 --precision bf16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_gb256_bf16.json 2>> gpurun_out/${TAG}_bench_stream_bf16.err; tail -c 300 gpurun_out/${TAG}_bench_gb256_bf16.json
