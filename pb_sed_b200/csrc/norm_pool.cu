@@ -297,53 +297,85 @@ __device__ __forceinline__ NbaCoef nba_coef(const float4* __restrict__ mean, con
   return k;
 }
 
-template <int U>        // rows in flight per thread: 4 for fp32 maps, 8 for bf16 maps (same bytes in flight)
+// BF = 0: fp32 maps, one channel quad (16 bytes) per thread and row; BF = 1: bf16 maps, TWO quads (8 channels = 16 bytes)
+// per thread and row, so both variants move 16 bytes per access and share the row arithmetic (32-bit: rows < 2^31).
+template <int BF>
 __global__ void __launch_bounds__(256)
 norm_bwd_apply4_kernel(const void* __restrict__ g, const void* __restrict__ x, int F, int T, int C4,
                        int per_f, const int* __restrict__ seq_len, const float4* __restrict__ mean,
                        const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                        const double* __restrict__ sums, float inv_n, void* __restrict__ dx,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch, int bf) {
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, long long total4, int nch) {
+  constexpr int NQ = BF ? 2 : 1, U = 4;
   if (inv_n <= 0.f) inv_n = (float)(1.0 / sums[2 * nch]);   // device-side count
-  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;       // multiple of C4 (256 % C4 == 0)
-  const int q = (int)(gtid % C4);
-  const long long rstep = stride / C4, rows = total4 / C4;
+  const unsigned CV = (unsigned)C4 / NQ;                      // channel vectors per row
+  const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;             // multiple of CV (256 % CV == 0)
+  const unsigned v = gtid % CV, q0 = v * NQ;
+  const unsigned rstep = stride / CV, rows = (unsigned)(total4 / C4);
   int f_cur = -1;
-  NbaCoef k;
-  if (!per_f) k = nba_coef(mean, rstd, gamma, sums, inv_n, q);
-  for (long long row0 = gtid / C4; row0 < rows; row0 += U * rstep) {
-    float4 gv[U], xv[U];
+  NbaCoef k[NQ];
+  if (!per_f) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) k[j] = nba_coef(mean, rstd, gamma, sums, inv_n, q0 + j);
+  }
+  for (unsigned row0 = gtid / CV; row0 < rows; row0 += U * rstep) {
+    float4 gv[U][NQ], xv[U][NQ];
     bool ok[U];
     int fr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long row = row0 + u * rstep;
+      const unsigned row = row0 + u * rstep;
       ok[u] = false;
       fr[u] = 0;
       if (row < rows) {
-        const int t = (int)(row % T);
-        const long long gq = row / T;
-        fr[u] = (int)(gq % F);
-        const int b = (int)(gq / F);
+        const unsigned t = row % (unsigned)T, gq = row / (unsigned)T;
+        fr[u] = (int)(gq % (unsigned)F);
+        const unsigned b = gq / (unsigned)F;
         const int len_b = seq_len ? min(__ldg(seq_len + b), T) : T;
-        ok[u] = t < len_b;
-        if (ok[u]) { gv[u] = ld_act4(g, 4 * (row * C4 + q), bf); xv[u] = ld_act4(x, 4 * (row * C4 + q), bf); }
+        ok[u] = (int)t < len_b;
+        if (ok[u]) {
+          const long long e = 4LL * ((long long)row * C4 + q0);
+          if (BF) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g) + e));
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + e));
+            gv[u][0] = bf16x4_to_float4(make_uint2(a.x, a.y)); gv[u][NQ - 1] = bf16x4_to_float4(make_uint2(a.z, a.w));
+            xv[u][0] = bf16x4_to_float4(make_uint2(c.x, c.y)); xv[u][NQ - 1] = bf16x4_to_float4(make_uint2(c.z, c.w));
+          } else {
+            gv[u][0] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g) + e));
+            xv[u][0] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + e));
+          }
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long row = row0 + u * rstep;
+      const unsigned row = row0 + u * rstep;
       if (row >= rows) break;
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r[NQ];
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok[u]) {
-        if (per_f && fr[u] != f_cur) { f_cur = fr[u]; k = nba_coef(mean, rstd, gamma, sums, inv_n, f_cur * C4 + q); }
-        r.x = fmaf(k.a.x, gv[u].x, fmaf(k.bx.x, xv[u].x, k.c0.x));
-        r.y = fmaf(k.a.y, gv[u].y, fmaf(k.bx.y, xv[u].y, k.c0.y));
-        r.z = fmaf(k.a.z, gv[u].z, fmaf(k.bx.z, xv[u].z, k.c0.z));
-        r.w = fmaf(k.a.w, gv[u].w, fmaf(k.bx.w, xv[u].w, k.c0.w));
+        if (per_f && fr[u] != f_cur) {
+          f_cur = fr[u];
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) k[j] = nba_coef(mean, rstd, gamma, sums, inv_n, f_cur * C4 + q0 + j);
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          r[j].x = fmaf(k[j].a.x, gv[u][j].x, fmaf(k[j].bx.x, xv[u][j].x, k[j].c0.x));
+          r[j].y = fmaf(k[j].a.y, gv[u][j].y, fmaf(k[j].bx.y, xv[u][j].y, k[j].c0.y));
+          r[j].z = fmaf(k[j].a.z, gv[u][j].z, fmaf(k[j].bx.z, xv[u][j].z, k[j].c0.z));
+          r[j].w = fmaf(k[j].a.w, gv[u][j].w, fmaf(k[j].bx.w, xv[u][j].w, k[j].c0.w));
+        }
       }
-      st_act4(dx, 4 * (row * C4 + q), r, bf);
+      const long long e = 4LL * ((long long)row * C4 + q0);
+      if (BF) {
+        const uint2 lo = float4_to_bf16x4(r[0]), hi = float4_to_bf16x4(r[NQ - 1]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dx) + e) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dx) + e) = r[0];
+      }
     }
   }
   if (blockIdx.x == 0 && dgamma) {
@@ -364,23 +396,24 @@ extern "C" int pbsed_norm_bwd_apply(const float* g, const float* x, int B, int F
   const float inv_count = count > 0. ? (float)(1.0 / count) : 0.f;   // <= 0: count = sums[2*nch] on the device
   const long long total = (long long)B * F * T * C;
   const int nch = per_f ? F * C : C;
-  if ((C & 3) == 0 && 256 % (C / 4) == 0 && ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
+  if ((C & (act_dtype == PBSED_BF16 ? 7 : 3)) == 0 && 256 % (C / 4) == 0 && total / C < (1LL << 31) &&
+      ((((uintptr_t)g) | ((uintptr_t)x) | ((uintptr_t)dx) | ((uintptr_t)save_mean) |
                         ((uintptr_t)save_rstd) | ((uintptr_t)gamma)) & 15) == 0) {
     const long long total4 = total / 4;
     int blocks4 = (int)((total4 + 255) / 256);
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;
     if (act_dtype == PBSED_BF16)
-      norm_bwd_apply4_kernel<8><<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+      norm_bwd_apply4_kernel<1><<<(blocks4 + 1) / 2, 256, 0, (cudaStream_t)stream>>>(
           g, x, F, T, C / 4, per_f, seq_len,
           reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
           reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
-          dgamma, dbeta, total4, nch, 1);
+          dgamma, dbeta, total4, nch);
     else
-      norm_bwd_apply4_kernel<4><<<blocks4, 256, 0, (cudaStream_t)stream>>>(
+      norm_bwd_apply4_kernel<0><<<blocks4, 256, 0, (cudaStream_t)stream>>>(
           g, x, F, T, C / 4, per_f, seq_len,
           reinterpret_cast<const float4*>(save_mean), reinterpret_cast<const float4*>(save_rstd),
           reinterpret_cast<const float4*>(gamma), sums, inv_count, dx,
-          dgamma, dbeta, total4, nch, 0);
+          dgamma, dbeta, total4, nch);
     return pbsed_after_launch();
   }
   if (act_dtype != PBSED_F32) return PBSED_EINVAL;
