@@ -91,7 +91,7 @@ def pipe(path):
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f'{a[1]:12.1f} {100 * a[1] / tot:5.1f}% {a[0]:5d} {a[2] / a[1]:8.1f} {a[3] / a[0] / 1e6:15.1f} '
               f'{a[3] / (a[1] * 1e-6) / 1e9:10.0f}  {k[:100]}')
-        if re.search(r'tapgemm_tc|wgrad_tc|tapgemm_pt|wgrad_mma', k):
+        if re.search(r'tapgemm_tc|tapgemm_fw|wgrad_tc|wgrad_tma|wgrad_mma', k):
             gemm_t += a[1]
             gemm_p += a[2]
     if gemm_t:
