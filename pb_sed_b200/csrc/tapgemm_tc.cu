@@ -80,6 +80,31 @@ wprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn
   }
 }
 
+// bf16 weight image (kind::f16 MMAs, 32 channels per stage): image[slice][tap][kb] = [k-chunk (4)][n (N)][8 bf16]; blobs keep
+// the spacing of the fp32 image (2 * KCH * N * 16 bytes) so the loader's arithmetic is shared
+__global__ void __launch_bounds__(256)
+wprep_bf16_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
+                  int ntaps, int Cin, int Cout, int N, __nv_bfloat16* __restrict__ img, double* __restrict__ rep,
+                  int rep_count) {
+  const int nkb = Cin / 32, n_slices = Cout / N;
+  const long long total = (long long)n_slices * ntaps * nkb * KCH * N * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rep_count; i += stride) rep[i] = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int e = (int)(i & 7);
+    long long q = i >> 3;
+    const int n = (int)(q % N); q /= N;
+    const int c = (int)(q % KCH); q /= KCH;
+    const int kb = (int)(q % nkb); q /= nkb;
+    const int tap = (int)(q % ntaps);
+    const int sl = (int)(q / ntaps);
+    const int cin = kb * 32 + c * 8 + e, cout = sl * N + n;
+    const float w = __ldg(W + (long long)tap * w_tap_stride + (long long)cout * w_sn + (long long)cin * w_sc);
+    const long long blob = ((long long)(sl * ntaps + tap) * nkb + kb) * (2LL * KCH * N * 8);     // in bf16 elements
+    img[blob + ((long long)c * N + n) * 8 + e] = __float2bfloat16_rn(w);
+  }
+}
+
 // fused column sums are accumulated into STAT_REP replicas (CTAs hash onto them) so that thousands of
 // CTAs do not serialise on the same few fp64 addresses in L2; this folds them into the caller's array
 constexpr int STAT_REP = 32;
@@ -102,7 +127,9 @@ struct __align__(16) SmemCtl {
 // 8 warps feed the big tiles faster; 4 keep more CTAs co-resident for the narrow, latency-bound layers.
 // IO: bit 0 = `in` is a bf16 map, bit 1 = `out` and `ep_src` are bf16 maps (compile-time, so the fp32
 // instantiations keep their register budget)
-template <int MT, int NBUF, int FW_PROD, int IO>
+// BFM = 1 (only with a bf16 `in`): operands go to shared memory as bf16, 32 channels per stage, ONE kind::f16 MMA per
+// k-step of 16 -- a sixth of the 3xTF32 instruction count
+template <int MT, int NBUF, int FW_PROD, int IO, int BFM>
 __global__ void __launch_bounds__(FW_PROD + 64, FW_PROD == 128 ? 4 : (MT <= 2 ? 2 : 1))   // MT <= 2: two CTAs per SM must stay resident (<= 96 registers)
 tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
@@ -114,6 +141,7 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
                   const int* __restrict__ load_seq_len, int t_super, int ctl_pad, int stat_n) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int IN_BF = IO & 1, OUT_BF = (IO >> 1) & 1;
+  static_assert(!BFM || IN_BF, "bf16 MMAs read a bf16 map");
   const int N = p.N;
   constexpr int RMAX = MT * TILE_M + 2 * HALO;         // strip rows
   constexpr uint32_t A_PART = KCH * RMAX * 16;         // bytes of one hi (or lo) strip stage
@@ -159,6 +187,69 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
     const int c = tid & 3;                                    // this thread's 16-byte k-chunk
     const int r0 = tid >> 2;
     const int nrows = mt_count * TILE_M + 2 * HALO;
+    if constexpr (BFM) {
+      // ---- bf16 operands: a thread's 16-byte chunk = 8 channels; loads stay packed (4 registers per row in flight)
+      uint4 vb[U];
+      float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sh1 = sh0;
+      int kb = 0, g = -1;
+      auto advance = [&]() -> bool {
+        while (true) {
+          if (++g == p.ngroups) { g = 0; ++kb; }
+          if (kb >= p.nkb) return false;
+          const int f = fo + p.g_df[g];
+          if (f >= 0 && f < p.F_in) return true;
+        }
+      };
+      auto issue = [&]() {
+        const int f_src = fo + p.g_df[g];
+        const long long src = ((long long)b * p.F_in + f_src) * p.T * p.in_stride + kb * 32 + c * 8;
+        if (scale) {
+          const int aff = (p.per_f ? f_src * p.Cin : 0) + kb * 32 + c * 8;
+          sc0 = __ldg(reinterpret_cast<const float4*>(scale + aff)); sc1 = __ldg(reinterpret_cast<const float4*>(scale + aff + 4));
+          sh0 = __ldg(reinterpret_cast<const float4*>(shift + aff)); sh1 = __ldg(reinterpret_cast<const float4*>(shift + aff + 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = r0 + RSTEP * u, t = t0 + r - HALO;
+          vb[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (r < nrows && t >= 0 && t < len_in)
+            vb[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + src + (long long)t * p.in_stride));
+        }
+      };
+      bool have = advance();
+      if (have) issue();
+      int it = 0;
+      while (have) {
+        const int slot = it % NA;
+        mbar_wait(&ctl->a_empty[slot], ((it / NA) & 1) ^ 1);
+        uint8_t* hi_base = a_smem + slot * A_STAGE;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = r0 + RSTEP * u, t = t0 + r - HALO;
+          if (r >= nrows) break;
+          uint4 o4 = vb[u];
+          if ((scale || p.relu) && t >= 0 && t < len_in) {
+            float4 x0 = bf16x4_to_float4(make_uint2(o4.x, o4.y)), x1 = bf16x4_to_float4(make_uint2(o4.z, o4.w));
+            if (scale) {
+              x0.x = fmaf(x0.x, sc0.x, sh0.x); x0.y = fmaf(x0.y, sc0.y, sh0.y); x0.z = fmaf(x0.z, sc0.z, sh0.z); x0.w = fmaf(x0.w, sc0.w, sh0.w);
+              x1.x = fmaf(x1.x, sc1.x, sh1.x); x1.y = fmaf(x1.y, sc1.y, sh1.y); x1.z = fmaf(x1.z, sc1.z, sh1.z); x1.w = fmaf(x1.w, sc1.w, sh1.w);
+            }
+            if (p.relu) {
+              x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+              x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+            }
+            const uint2 lo2 = float4_to_bf16x4(x0), hi2 = float4_to_bf16x4(x1);
+            o4 = make_uint4(lo2.x, lo2.y, hi2.x, hi2.y);
+          }
+          *reinterpret_cast<uint4*>(hi_base + (uint32_t)(c * RMAX + r) * 16) = o4;
+        }
+        fence_async_smem();
+        mbar_arrive(&ctl->a_full[slot]);
+        ++it;
+        have = advance();
+        if (have) issue();
+      }
+    } else {
     float4 v[U];
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     int kb = 0, g = -1;
@@ -225,6 +316,7 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
       ++it;
       have = advance();
       if (have) issue();
+    }
     }
     // ============================== epilogue ==============================
     // TMEM -> registers (thread = frame) -> bias / ReLU-mask -> shared-memory tile -> (a) row-contiguous
@@ -343,7 +435,7 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
   } else if (warp == FW_PROD / 32) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(TILE_M, N);
+      const uint32_t idesc = BFM ? make_idesc_bf16(TILE_M, N) : make_idesc_tf32(TILE_M, N);
       const uint32_t a_lbo = RMAX * 16, b_lbo = (uint32_t)N * 16;
       const uint64_t a_d0 = make_desc(0, a_lbo, 128), b_d0 = make_desc(0, b_lbo, 128);
       int it = 0, bt = 0;
@@ -368,6 +460,7 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
               for (int ks = 0; ks < KB / 8; ++ks) {
                 const uint32_t ao = arow + (uint32_t)(ks * 2) * a_lbo, bo = (uint32_t)(ks * 2) * b_lbo;
                 const uint64_t dah = desc_at(a_d0, a_hi + ao), dbh = desc_at(b_d0, b_hi + bo);
+                if (BFM) { mma_bf16(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u); continue; }
                 mma_tf32(d, dah, dbh, idesc, (first && ks == 0) ? 0u : 1u);
                 if (!p.single) {
                   mma_tf32(d, desc_at(a_d0, a_lo + ao), dbh, idesc, 1u);
@@ -397,7 +490,7 @@ tapgemm_tc_kernel(TcParams p, const void* __restrict__ in, const float* __restri
             const int bslot = bt % NBUF;
             mbar_wait(&ctl->b_empty[bslot], ((bt / NBUF) & 1) ^ 1);
             const long long blob = ((long long)(slice * p.ntaps + p.g_tap[g][j]) * p.nkb + kb) * (long long)(B_STAGE / 4);
-            const uint32_t nbytes = p.single ? B_PART : B_STAGE;     // the hi image leads every blob
+            const uint32_t nbytes = (p.single || BFM) ? B_PART : B_STAGE;     // the hi (or bf16) image leads every blob
             mbar_expect_tx(&ctl->b_full[bslot], nbytes);
             bulk_g2s(b_smem + bslot * B_STAGE, img + blob, nbytes, &ctl->b_full[bslot]);
             ++bt;
@@ -1040,7 +1133,10 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   p.out_stride = d->out_stride > 0 ? d->out_stride : d->Cout;
   p.N = d->Cout < NSLICE ? d->Cout : NSLICE;
   p.n_slices = d->Cout / p.N;
-  p.nkb = d->Cin / KB;
+  // bf16 input map + reduced precision + 32-channel blocks: bf16 MMAs (kind::f16); otherwise TF32 passes
+  static const int use_bfm = getenv("PBSED_BF16_MMA") ? atoi(getenv("PBSED_BF16_MMA")) : 1;
+  const bool bfm = use_bfm && d->in_dtype == PBSED_BF16 && d->precision == 3 && d->Cin % 32 == 0;
+  p.nkb = d->Cin / (bfm ? 32 : KB);
   p.ntaps = d->ntaps;
   p.single = d->precision == 3;
   // group taps by df
@@ -1059,8 +1155,12 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
     const long long total = (long long)d->ntaps * d->Cin * d->Cout;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img,
-                                         rep, want_sums ? STAT_REP * stat_n * 2 : 0, p.single);
+    if (bfm)
+      wprep_bf16_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N,
+                                                reinterpret_cast<__nv_bfloat16*>(img), rep, want_sums ? STAT_REP * stat_n * 2 : 0);
+    else
+      wprep_kernel<<<blocks, 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, d->ntaps, d->Cin, d->Cout, p.N, img,
+                                           rep, want_sums ? STAT_REP * stat_n * 2 : 0, p.single);
     int rc = pbsed_after_launch();
     if (rc) return rc;
   }
@@ -1084,18 +1184,20 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   if (grid.y > 65535 || grid.z > 65535) return 0;
   cudaError_t e;
   const int io = (d->in_dtype == PBSED_BF16 ? 1 : 0) | (d->out_dtype == PBSED_BF16 ? 2 : 0);
-#define PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, IOV)                                                        \
-  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV, NBV, PRV, IOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+#define PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, IOV, BFV)                                                   \
+  e = cudaFuncSetAttribute(tapgemm_tc_kernel<MTV, NBV, PRV, IOV, BFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return (int)e;                                                                 \
-  tapgemm_tc_kernel<MTV, NBV, PRV, IOV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
+  tapgemm_tc_kernel<MTV, NBV, PRV, IOV, BFV><<<grid, PRV + 64, smem, st>>>(p, in, scale, shift, seq_len, img, bias, out, ep_src,  \
                                                   ep_scale, ep_shift, out_stats, ep_mean, ep_rstd, ep_sums, \
                                                   d->no_input_mask ? nullptr : seq_len, t_super, (int)pad, stat_n);
 #define PBSED_TC_LAUNCH(MTV, NBV, PRV)                                                                \
-  switch (io) {                                                                                       \
-    case 0: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 0) } break;                                           \
-    case 1: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 1) } break;                                           \
-    case 2: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 2) } break;                                           \
-    default: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 3) } break;                                          \
+  switch (io + (bfm ? 4 : 0)) {                                                                       \
+    case 0: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 0, 0) } break;                                        \
+    case 1: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 1, 0) } break;                                        \
+    case 2: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 2, 0) } break;                                        \
+    case 3: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 3, 0) } break;                                        \
+    case 5: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 1, 1) } break;                                        \
+    default: { PBSED_TC_LAUNCH_IO(MTV, NBV, PRV, 3, 1) } break;                                       \
   }
   pbsed_note_kernel(nbuf == 2 ? "tapgemm_tc_kernel<2,2,256>" : mt == 4 ? "tapgemm_tc_kernel<4,4,256>" : mt == 2 ? "tapgemm_tc_kernel<2,4,256>"
                     : p.N <= 32 ? "tapgemm_tc_kernel<1,4,128>" : "tapgemm_tc_kernel<1,4,256>");

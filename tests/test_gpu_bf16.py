@@ -48,7 +48,9 @@ def test_bf16_maps_forward_dgrad_wgrad_vs_fp32_kernels(B, F, T, Cin, Cout, taps,
     stats = torch.zeros(Cout, 2, device=DEV, dtype=torch.float64)
     out = ops.tapgemm(x, W, bias, desc, scale, shift, seq, out_stats=stats)
     assert out.dtype == odt
-    assert reldiff(out.float(), ref) < 1.2e-2             # TF32-rounded weights + one bf16 rounding of the output
+    # bf16 activations x bf16 weights (kind::f16, where the input map is bf16 and Cin % 32 == 0; TF32-rounded weights
+    # otherwise) + one bf16 rounding of the output
+    assert reldiff(out.float(), ref) < 2e-2
     st_ref = torch.zeros(Cout, 2, device=DEV, dtype=torch.float64)
     ops.call('pbsed_channel_stats', ops._ptr(ref), B, F, T, Cout, 0, seq.ptr, ops._ptr(st_ref), 0, ops._stream())
     assert reldiff(stats, st_ref) < 5e-3                  # statistics come from the fp32 accumulators
@@ -61,7 +63,7 @@ def test_bf16_maps_forward_dgrad_wgrad_vs_fp32_kernels(B, F, T, Cin, Cout, taps,
                           out_dtype=ops._dt(idt))
     g = ops.tapgemm(dz, W, None, ddesc, None, None, seq, ep_src=x, ep_scale=scale, ep_shift=shift)
     assert g.dtype == idt
-    assert reldiff(g.float(), g_ref) < 1.2e-2
+    assert reldiff(g.float(), g_ref) < 2e-2
     # weight gradient
     res = []
     for prec, xx, zz, kw in ((0, x.float(), dz.float(), {}), (3, x, dz, dict(in_dtype=ops._dt(idt), out_dtype=ops._dt(odt)))):
