@@ -348,6 +348,33 @@ static int launch_gru_bc(const int* seq_len, int B, int T, int ndir, const GruDi
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+// how many clusters of H/32 CTAs are co-resident on THIS device (an 8-CTA cluster needs 8 free SMs of one GPC: 14 on
+// the B200s measured); asked from the runtime once per kernel variant, sized for the smallest clips-per-cluster variant
+template <int H, bool BWD>
+static int gru_max_clusters() {
+  static int cached = 0;
+  if (cached) return cached;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H / 32, 64, 1);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = BWD ? (size_t)(2 * 3 * 4 * H + 8 * 4 * 32) * sizeof(float) : 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = H / 32; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e;
+  if (BWD) {
+    cudaFuncSetAttribute(gru_bwd_kernel<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    e = cudaOccupancyMaxActiveClusters(&n, gru_bwd_kernel<H, 4>, &cfg);
+  } else {
+    e = cudaOccupancyMaxActiveClusters(&n, gru_fwd_kernel<H, 4>, &cfg);
+  }
+  if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = (H / 32 == 8) ? 14 : 148 / (H / 32); }
+  cached = n;
+  return n;
+}
+
 // clips per cluster: 8 (measured faster than 4 at B = 32 even though 4 halves the FMAs per step;
 // PBSED_GRU_BC=4 forces the other variant for experiments)
 template <int H, bool BWD>
@@ -359,7 +386,7 @@ static int launch_gru(const int* seq_len, int B, int T, int ndir, const GruDirs&
     // fewest clips per cluster whose clusters are all co-resident: an 8-CTA cluster needs 8 free SMs of
     // one GPC and ~14 of them fit a B200 at once (16 clusters of the 4-clip variant at B = 32 ran in two
     // rounds = 2x the time); fewer clips = fewer FMAs on the 500-step critical path
-    const int max_clusters = (H / 32 == 8) ? 14 : 148 / (H / 32);
+    const int max_clusters = gru_max_clusters<H, BWD>();
     bc = 8;
     for (int c : {4, 5, 6}) if (cdiv(B, c) * ndir <= max_clusters) { bc = c; break; }
   }

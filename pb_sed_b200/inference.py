@@ -12,6 +12,8 @@ to the caller (``NotImplementedError`` if requested here).
 """
 from math import ceil
 
+import re
+
 import numpy as np
 import torch
 
@@ -50,24 +52,32 @@ def segment_batch(batch, max_length, overlap, keys=('stft',), axis=2):
     return segments
 
 
+_SEGMENT_ID = re.compile(r'^(?P<base>.*)_!segment!_(?P<index>\d+)_(?P<count>\d+)$')
+
+
 def merge_segments(segmental_output, segment_overlap):
-    """pb_sed/utils/segment.py:50-72."""
-    merged = {}
-    for audio_id in sorted(segmental_output.keys()):
-        if '_!segment!_0_' in audio_id:
-            audio_id, n_segments = audio_id.split('_!segment!_0_')
-            n_segments = int(n_segments)
-            parts = []
-            for i in range(n_segments):
-                arr = segmental_output[f'{audio_id}_!segment!_{i}_{n_segments}']
-                if i < (n_segments - 1) and segment_overlap > 0:
-                    arr = arr[..., :-ceil(segment_overlap / 2), :]
-                if i > 0 and segment_overlap > 0:
-                    arr = arr[..., segment_overlap // 2:, :]
-                parts.append(arr)
-            merged[audio_id] = np.concatenate(parts, axis=-2)
-        elif '_!segment!_' not in audio_id:
-            merged[audio_id] = segmental_output[audio_id]
+    """stitch per-segment score arrays (frames on axis -2) back into one array per clip; same contract as
+    pb_sed/utils/segment.py:50-72: ids ``<clip>_!segment!_<i>_<n>``, neighbouring segments share
+    ``segment_overlap`` frames, of which the left segment keeps the first half (rounded down) and the right one the rest;
+    ids without the segment suffix pass through."""
+    groups, merged = {}, {}
+    for key, value in segmental_output.items():
+        m = _SEGMENT_ID.match(key)
+        if m is None:
+            merged[key] = value
+        else:
+            groups.setdefault(m['base'], {})[int(m['index'])] = (int(m['count']), value)
+    drop_right, drop_left = ((segment_overlap + 1) // 2, segment_overlap // 2) if segment_overlap > 0 else (0, 0)
+    for base in sorted(groups):
+        parts = groups[base]
+        count = parts[0][0]
+        pieces = []
+        for i in range(count):
+            arr = parts[i][1]
+            lo = drop_left if i > 0 else 0
+            hi = arr.shape[-2] - (drop_right if i < count - 1 else 0)
+            pieces.append(arr[..., lo:hi, :])
+        merged[base] = np.concatenate(pieces, axis=-2)
     return merged
 
 
