@@ -36,8 +36,7 @@ conv_cin1_fwd_kernel(Cin1Params p, const float* __restrict__ in, const float* __
   for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = bias ? __ldg(bias + i) : 0.f;
   __syncthreads();
   const int fo = blockIdx.y, b = blockIdx.z;
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= p.T) return;
+  const int t = blockIdx.x * 256 + threadIdx.x;           // frames >= T compute on (masked) padding and store nothing
   const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
   const bool affine = scale != nullptr;
   const float sc = affine ? __ldg(scale) : 1.f, sh = affine ? __ldg(shift) : 0.f;
@@ -49,10 +48,28 @@ conv_cin1_fwd_kernel(Cin1Params p, const float* __restrict__ in, const float* __
 #pragma unroll
     for (int n = 0; n < COUT; ++n) acc[n] = fmaf(a, ws[tap][n], acc[n]);
   }
-  const long long o = (((long long)b * p.F_out + fo) * p.T + t) * p.out_stride;
+  // stores: a thread owns one frame's COUT channels (64 / 128 bytes, lanes 64 / 128 bytes apart); the warp's 32 frames are
+  // contiguous in memory, so the tile goes through shared memory and leaves as fully coalesced 16-byte-per-lane rows
+  __shared__ __align__(16) float tile[8][32][COUT + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int n = 0; n < COUT; n += 4)
-    st_act4(out, o + n, make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]), p.out_bf16);
+    *reinterpret_cast<float4*>(&tile[warp][lane][n]) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+  __syncwarp();
+  const int t_w = blockIdx.x * 256 + warp * 32;                      // first frame of this warp
+  const long long o = (((long long)b * p.F_out + fo) * p.T + t_w) * p.out_stride;
+  constexpr int Q = COUT / 4;
+  if (p.out_stride == COUT) {
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const int i = lane + 32 * k, fr = i / Q, q = i % Q;
+      if (t_w + fr < p.T) st_act4(out, o + (long long)fr * COUT + 4 * q, *reinterpret_cast<const float4*>(&tile[warp][fr][4 * q]), p.out_bf16);
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < COUT; n += 4)
+      st_act4(out, o + (long long)lane * p.out_stride + n, make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]), p.out_bf16);
+  }
 }
 
 // dW[tap][n] += sum_rows dout[row][n] * a[row + off(tap)];  dbias[n] += sum_rows dout[row][n]
@@ -65,17 +82,19 @@ conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* 
                        const float* __restrict__ shift, const int* __restrict__ seq_len,
                        const float* __restrict__ dout, int mask_out, float* __restrict__ dW,
                        float* __restrict__ dbias, int groups_per_cta, int df_min, int n_rows, int dt_min, int halo) {
-  constexpr int RL = 256 / COUT;
+  // thread = (frame lane rl, channel QUAD q): one 16-byte (8-byte bf16) dout load feeds 4 x ntaps FMAs, the strip value of
+  // a tap is read once per quad instead of once per channel
+  constexpr int Q = COUT / 4, RL = 256 / Q, RW = 32 / Q;     // frame lanes per CTA / per warp
   extern __shared__ float strip[];                         // [n_rows][T + halo]
-  __shared__ float red[PBSED_MAX_TAPS + 1][256];
-  const int n = threadIdx.x % COUT, rl = threadIdx.x / COUT;
+  __shared__ float4 red[8][PBSED_MAX_TAPS + 1][Q];
+  const int q = threadIdx.x % Q, rl = threadIdx.x / Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool affine = scale != nullptr;
   const float sc = affine ? __ldg(scale) : 1.f, sh = affine ? __ldg(shift) : 0.f;
   const int LD = p.T + halo;
-  float acc[PBSED_MAX_TAPS];
+  float4 acc[PBSED_MAX_TAPS + 1];                           // [ntaps] = bias sum
 #pragma unroll
-  for (int i = 0; i < PBSED_MAX_TAPS; ++i) acc[i] = 0.f;
-  float bsum = 0.f;
+  for (int i = 0; i <= PBSED_MAX_TAPS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int total = p.B * p.F_out;
   const int g0 = blockIdx.x * groups_per_cta, g1 = min(g0 + groups_per_cta, total);
   for (int g = g0; g < g1; ++g) {
@@ -88,27 +107,46 @@ conv_cin1_wgrad_kernel(Cin1Params p, const float* __restrict__ in, const float* 
       strip[i] = cin1_load(in, p, b, fo + df_min + r, tt + dt_min, len_b, sc, sh, affine);
     }
     __syncthreads();
-    const long long z0 = ((long long)b * p.F_out + fo) * p.T * p.out_stride + n;
+    const long long z0 = ((long long)b * p.F_out + fo) * p.T * p.out_stride + 4 * q;
     for (int t = rl; t < len_out; t += RL) {
-      const float dz = ld_act1(dout, z0 + (long long)t * p.out_stride, p.out_bf16);
-      bsum += dz;
+      const float4 dz = ld_act4(dout, z0 + (long long)t * p.out_stride, p.out_bf16);
+      acc[PBSED_MAX_TAPS].x += dz.x; acc[PBSED_MAX_TAPS].y += dz.y; acc[PBSED_MAX_TAPS].z += dz.z; acc[PBSED_MAX_TAPS].w += dz.w;
 #pragma unroll
       for (int tap = 0; tap < PBSED_MAX_TAPS; ++tap) {
-        if (tap < p.ntaps)
-          acc[tap] = fmaf(dz, strip[(p.df[tap] - df_min) * LD + t + p.dt[tap] - dt_min], acc[tap]);
+        if (tap < p.ntaps) {
+          const float a = strip[(p.df[tap] - df_min) * LD + t + p.dt[tap] - dt_min];
+          acc[tap].x = fmaf(dz.x, a, acc[tap].x); acc[tap].y = fmaf(dz.y, a, acc[tap].y);
+          acc[tap].z = fmaf(dz.z, a, acc[tap].z); acc[tap].w = fmaf(dz.w, a, acc[tap].w);
+        }
       }
     }
   }
-  for (int tap = 0; tap < p.ntaps; ++tap) red[tap][threadIdx.x] = acc[tap];
-  red[PBSED_MAX_TAPS][threadIdx.x] = bsum;
+  // reduce over the frame lanes: shuffles inside the warp (lanes q + Q * k), then the 8 warps through shared memory
+#pragma unroll
+  for (int tap = 0; tap <= PBSED_MAX_TAPS; ++tap) {
+    if (tap < p.ntaps || tap == PBSED_MAX_TAPS) {
+      float4 v = acc[tap];
+#pragma unroll
+      for (int o = Q; o < 32; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+      }
+      if (lane < Q) red[warp][tap][lane] = v;
+    }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < (p.ntaps + 1) * COUT; i += 256) {
-    const int tap = i / COUT, nn = i % COUT;
-    const int row = tap < p.ntaps ? tap : PBSED_MAX_TAPS;
-    float s = 0.f;
-    for (int r = 0; r < RL; ++r) s += red[row][r * COUT + nn];
-    if (tap < p.ntaps) { if (s != 0.f) atomicAdd(dW + tap * COUT + nn, s); }
-    else if (dbias && s != 0.f) atomicAdd(dbias + nn, s);
+  for (int i = threadIdx.x; i < (PBSED_MAX_TAPS + 1) * Q; i += 256) {
+    const int tap = i / Q, qq = i % Q;
+    if (tap >= p.ntaps && tap != PBSED_MAX_TAPS) continue;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < 8; ++w) { const float4 u = red[w][tap][qq]; s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
+    float* dst = tap < p.ntaps ? dW + tap * COUT + 4 * qq : (dbias ? dbias + 4 * qq : nullptr);
+    if (dst) {
+      if (s.x != 0.f) atomicAdd(dst + 0, s.x);
+      if (s.y != 0.f) atomicAdd(dst + 1, s.y);
+      if (s.z != 0.f) atomicAdd(dst + 2, s.z);
+      if (s.w != 0.f) atomicAdd(dst + 3, s.w);
+    }
   }
 }
 
