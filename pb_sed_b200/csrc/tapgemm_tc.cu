@@ -1087,6 +1087,254 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
   }
 }
 
+
+// =====================================================================================
+// wgrad_bf16_kernel: the weight gradient of the 'bf16' mode -- both operands are bf16 maps, the MMAs are kind::f16
+// (bf16 x bf16 -> fp32, K = 16 frames per instruction).  Same structure as wgrad_tma_kernel (TMA raw ring -> converter
+// warps -> K-major operand images -> tcgen05), with twice the frames per stage and half the MMAs per frame:
+//   stage = 64 frames; chunk j = frames { t0 + j + 8 i, i = 0..7 } = one 16-byte row of 8 bf16; dout chunks j = 0..7,
+//   input chunks j = -1..8 (the dt = -1/0/+1 taps are whole-chunk shifts, as before); an MMA k-step = two chunks.
+// dout needs no arithmetic at all (mask + 16-bit transposition), the input goes bf16 -> fp32 (norm, ReLU) -> bf16.
+constexpr int WB_KR = 64, WB_AROWS = WB_KR + 2, WB_STAGES = 3, WB_RAW = 3;
+
+struct __align__(16) WbCtl {
+  uint64_t full[WB_STAGES], empty[WB_STAGES], raw_full[WB_RAW], raw_empty[WB_RAW], acc_full;
+  uint32_t tmem_base;
+};
+
+// 8 frames x 4 channels (one uint2 of 4 bf16 per frame) -> 4 rows of 8 bf16 (one uint4 per channel)
+__device__ __forceinline__ void bf16_transpose_8x4(const uint2 (&v)[8], uint4 (&o)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = (c < 2) ? v[2 * i].x : v[2 * i].y, b = (c < 2) ? v[2 * i + 1].x : v[2 * i + 1].y;
+      w[i] = (c & 1) ? __byte_perm(a, b, 0x7632) : __byte_perm(a, b, 0x5410);     // high / low halves of (a, b)
+    }
+    o[c] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(WG_PROD + 64)
+wgrad_bf16_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_a,
+                  const float* __restrict__ scale, const float* __restrict__ shift, const int* __restrict__ seq_len,
+                  const void* __restrict__ dout, float* __restrict__ dW, float* __restrict__ dbias) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int zq = p.Ms / 4, aq = p.Nc / 4;
+  const uint32_t Z_LBO = 128 * 16, A_LBO = (uint32_t)p.Nc * 16;
+  const uint32_t Z_PART = WG_ZCH * Z_LBO, A_PART = WG_ACH * A_LBO;
+  const uint32_t STAGE = Z_PART + A_PART;
+  const uint32_t RAW_Z = WB_KR * (uint32_t)p.Ms * 2, RAW_A = WB_AROWS * (uint32_t)p.Nc * 2;
+  const uint32_t RAW = RAW_Z + RAW_A;
+  uint8_t* raw_base = smem_raw + WB_STAGES * STAGE;
+  WbCtl* ctl = reinterpret_cast<WbCtl*>(raw_base + WB_RAW * RAW);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int c_slice = blockIdx.z % p.c_slices, m_slice = blockIdx.z / p.c_slices;
+  const int m0 = m_slice * p.Ms, c0 = c_slice * p.Nc;
+  const int df = p.g_df[g], ntap = p.g_n[g];
+  const int t_blocks = (p.T + WG_TB - 1) / WG_TB;
+  const int total_units = p.B * p.F_out * t_blocks;
+  const bool do_bias = dbias != nullptr && g == 0 && c_slice == 0;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ntap * p.Nc) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < WB_STAGES; ++i) { mbar_init(&ctl->full[i], WG_PROD); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < WB_RAW; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], WG_PROD); }
+    mbar_init(&ctl->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_PROD / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (p.Ms < 128) {      // operand rows m >= Ms are read by the M = 128 MMA but never produced: zero once
+    for (int s = 0; s < WB_STAGES; ++s)
+      for (int ch = 0; ch < WG_ZCH; ++ch) {
+        uint4* base = reinterpret_cast<uint4*>(smem_raw + s * STAGE + ch * Z_LBO);
+        for (int i = p.Ms + tid; i < 128; i += WG_PROD + 64) base[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < WG_PROD / 32) {
+    // ============================== converters ==============================
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int zqi = tid % zq, aqi = tid % aq;
+    const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+      const int tb = u % t_blocks, gq = u / t_blocks;
+      const int fo = gq % p.F_out, b = gq / p.F_out;
+      const int f_src = fo + df;
+      const bool f_ok = f_src >= 0 && f_src < p.F_in;
+      if (!f_ok && !do_bias) continue;
+      const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
+      const int len_out = p.mask_out ? len_b : p.T;
+      const int t_end = min(p.T, (tb + 1) * WG_TB);
+      if (!f_ok) {                                 // bias-only visit of a border row group: plain loads
+        const long long zsrc = ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
+        for (int t = tb * WG_TB + zj0; t < t_end; t += zjs)
+          if (t < len_out) {
+            const float4 v = ld_act4(dout, zsrc + (long long)t * p.out_stride, 1);
+            bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+          }
+        continue;
+      }
+      if (scale) {
+        const int aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
+        sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
+        sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
+      }
+      for (int t0 = tb * WG_TB; t0 < t_end; t0 += WB_KR, ++it) {
+        const int rs = it % WB_RAW, slot = it % WB_STAGES;
+        const uint8_t* rz = raw_base + (uint32_t)rs * RAW;
+        const uint8_t* ra = rz + RAW_Z;
+        uint8_t* z_img = smem_raw + slot * STAGE;
+        uint8_t* a_img = z_img + Z_PART;
+        mbar_wait(&ctl->raw_full[rs], (it / WB_RAW) & 1);
+        mbar_wait(&ctl->empty[slot], ((it / WB_STAGES) & 1) ^ 1);
+        for (int j = zj0; j < WG_ZCH; j += zjs) {
+          uint2 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = j + 8 * i;
+            v[i] = make_uint2(0u, 0u);
+            if (t0 + r < len_out) v[i] = *reinterpret_cast<const uint2*>(rz + 2 * (uint32_t)(r * p.Ms + zqi * 4));
+            if (do_bias) { const float4 f = bf16x4_to_float4(v[i]); bsum.x += f.x; bsum.y += f.y; bsum.z += f.z; bsum.w += f.w; }
+          }
+          uint4 o[4];
+          bf16_transpose_8x4(v, o);
+          const uint32_t ob = (uint32_t)j * Z_LBO + (uint32_t)zqi * 16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(z_img + ob + k * zq * 16) = o[k];
+        }
+        for (int jj = aj0; jj < WG_ACH; jj += ajs) {
+          uint2 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = jj + 8 * i, t = t0 + r - 1;
+            v[i] = make_uint2(0u, 0u);
+            if (t >= 0 && t < len_b) {
+              v[i] = *reinterpret_cast<const uint2*>(ra + 2 * (uint32_t)(r * p.Nc + aqi * 4));
+              if (scale || p.relu) {
+                float4 x = bf16x4_to_float4(v[i]);
+                if (scale) {
+                  x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                  x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                }
+                if (p.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                v[i] = float4_to_bf16x4(x);
+              }
+            }
+          }
+          uint4 o[4];
+          bf16_transpose_8x4(v, o);
+          const uint32_t ob = (uint32_t)jj * A_LBO + (uint32_t)aqi * 16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(a_img + ob + k * aq * 16) = o[k];
+        }
+        mbar_arrive(&ctl->raw_empty[rs]);
+        fence_async_smem();
+        mbar_arrive(&ctl->full[slot]);
+      }
+    }
+    if (do_bias) {
+      float* db = dbias + m0 + zqi * 4;
+      if (bsum.x != 0.f) atomicAdd(db + 0, bsum.x);
+      if (bsum.y != 0.f) atomicAdd(db + 1, bsum.y);
+      if (bsum.z != 0.f) atomicAdd(db + 2, bsum.z);
+      if (bsum.w != 0.f) atomicAdd(db + 3, bsum.w);
+    }
+    // ============================== epilogue ==============================
+    mbar_wait(&ctl->acc_full, 0);
+    tc_fence_after();
+    const int lw = warp & 3, half = warp >> 2;
+    const int m = lw * 32 + lane;
+    const int n = m0 + 4 * (m % zq) + m / zq;
+    if (it > 0) {
+      for (int j = 0; j < ntap; ++j) {
+        float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
+        for (int cc = half * 16; cc < p.Nc; cc += 32) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
+          if (m < p.Ms) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int ci = cc + k;
+              const int c = c0 + 4 * (ci % aq) + ci / aq;
+              if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == WG_PROD / 32) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TILE_M, p.Nc);
+      const uint64_t z_d0 = make_desc(0, Z_LBO, 128), a_d0 = make_desc(0, A_LBO, 128);
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out;
+        const int f_src = fo + df;
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WB_KR) {
+          const int slot = it % WB_STAGES;
+          mbar_wait(&ctl->full[slot], (it / WB_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t z_img = smem_u32(smem_raw + slot * STAGE), a_img = z_img + Z_PART;
+          for (int j = 0; j < ntap; ++j) {
+            const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
+            const int dt = p.g_dt[g][j];
+#pragma unroll
+            for (int ks = 0; ks < WG_ZCH / 2; ++ks)
+              mma_bf16(d, desc_at(z_d0, z_img + (uint32_t)(2 * ks) * Z_LBO), desc_at(a_d0, a_img + (uint32_t)(2 * ks + dt + 1) * A_LBO),
+                       idesc, (it == 0 && ks == 0) ? 0u : 1u);
+          }
+          mma_commit(&ctl->empty[slot]);
+          ++it;
+        }
+      }
+      mma_commit(&ctl->acc_full);
+    }
+  } else {
+    // ============================== TMA loader ==============================
+    if (lane == 0) {
+      int it = 0;
+      for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
+        const int tb = u % t_blocks, gq = u / t_blocks;
+        const int fo = gq % p.F_out, b = gq / p.F_out;
+        const int f_src = fo + df;
+        if (f_src < 0 || f_src >= p.F_in) continue;
+        const int t_end = min(p.T, (tb + 1) * WG_TB);
+        const int zrow = (b * p.F_out + fo) * p.T, arow = (b * p.F_in + f_src) * p.T;
+        for (int t0 = tb * WG_TB; t0 < t_end; t0 += WB_KR, ++it) {
+          const int rs = it % WB_RAW;
+          mbar_wait(&ctl->raw_empty[rs], ((it / WB_RAW) & 1) ^ 1);
+          uint8_t* dst = raw_base + (uint32_t)rs * RAW;
+          mbar_expect_tx(&ctl->raw_full[rs], RAW);
+          tma_load_2d(dst, &tm_z, m0, zrow + t0, &ctl->raw_full[rs]);
+          tma_load_2d(dst + RAW_Z, &tm_a, c0, arow + t0 - 1, &ctl->raw_full[rs]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == WG_PROD / 32) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace
 
 // per-row-tile "first" flag: the first MMA into EACH accumulator must overwrite.  The loop above
@@ -1251,6 +1499,29 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   // ---- TMA-fed variant (default): raw tiles by tensor-map loads, as many raw stages as shared memory holds
   static const int use_tma = getenv("PBSED_WG_TMA") ? atoi(getenv("PBSED_WG_TMA")) : 1;
   const long long rows_z = (long long)p.B * p.F_out * p.T, rows_a = (long long)p.B * p.F_in * p.T;
+  // ---- 'bf16' mode: both maps bf16 -> kind::f16 MMAs over 64-frame stages
+  static const int use_wb = getenv("PBSED_BF16_MMA") ? atoi(getenv("PBSED_BF16_MMA")) : 1;
+  if (use_wb && use_tma && p.in_bf16 && p.out_bf16 && p.single && rows_z < (1LL << 31) && rows_a < (1LL << 31)) {
+    const size_t wstage = (size_t)WG_ZCH * 128 * 16 + (size_t)WG_ACH * p.Nc * 16;
+    const size_t wraw = (size_t)WB_KR * p.Ms * 2 + (size_t)WB_AROWS * p.Nc * 2;
+    const size_t smem = WB_STAGES * wstage + WB_RAW * wraw + sizeof(WbCtl) + 128;
+    CUtensorMap tm_z, tm_a;
+    if (smem <= 227 * 1024 &&
+        make_tmap_2d(&tm_z, dout, p.Cout, rows_z, p.out_stride, p.Ms, WB_KR, 1) &&
+        make_tmap_2d(&tm_a, in, p.Cin, rows_a, p.in_stride, p.Nc, WB_AROWS, 1)) {
+      int rs = 148 / roles;
+      if (rs > units) rs = units;
+      if (rs < 1) rs = 1;
+      p.row_splits = rs;
+      cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      dim3 grid(rs, p.ngroups, p.m_slices * p.c_slices);
+      pbsed_note_kernel("wgrad_bf16_kernel");
+      wgrad_bf16_kernel<<<grid, WG_PROD + 64, smem, st>>>(p, tm_z, tm_a, scale, shift, seq_len, dout, dW, dbias);
+      *handled = 1;
+      return pbsed_after_launch();
+    }
+  }
   if (use_tma && rows_z < (1LL << 31) && rows_a < (1LL << 31)) {
     const size_t raw = (size_t)WG_KR * p.Ms * (p.out_bf16 ? 2 : 4) + (size_t)WG_RAW_AROWS * p.Nc * (p.in_bf16 ? 2 : 4);
     const size_t budget = 227 * 1024 - WG_STAGES * stage - sizeof(WgTmaCtl) - 256;
