@@ -22,9 +22,10 @@ import os
 PRECISION = {'fp32': 0, 'tf32x3': 1, 'tf32': 3, 'bf16': 3}
 _default_precision = PRECISION[os.environ.get('PBSED_PRECISION', 'tf32x3')]
 # storage type of the conv-stack activation maps and their gradients in HBM: torch.float32, or torch.bfloat16 in
-# the 'bf16' mode (BASELINE configs[2] / [4]).  In that mode the conv stacks run ONE tensor-core pass: bf16
-# activations (exact in the kind::tf32 operand format) times TF32-rounded weights, fp32 accumulation; master weights,
-# batch statistics, the GRU and the optimizer stay fp32.
+# the 'bf16' mode (BASELINE configs[2] / [4]).  In that mode the conv stacks run ONE tensor-core pass with fp32
+# accumulation: kind::f16 (bf16 x bf16, K = 16) MMAs wherever the input map is bf16 with a multiple of 32 channels
+# (forward, data and weight gradients of the wide layers), one kind::tf32 pass on the bf16-exact values elsewhere; master
+# weights, batch statistics, the GRU and the optimizer stay fp32.
 _act_dtype = torch.bfloat16 if os.environ.get('PBSED_PRECISION') == 'bf16' else torch.float32
 
 
