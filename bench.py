@@ -370,8 +370,9 @@ def run_gpu(args):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': scaling, 'vs_baseline': None, 'dtype': {'fp32': 'f32', 'tf32x3': 'f32 via 3xTF32 split (tcgen05, fp32 accumulate)',
                       'tf32': 'tf32 single pass (tcgen05, fp32 accumulate; reduced precision >= bf16 mantissa)',
-                      'bf16': 'bf16 (conv-stack activations + gradients stored as bf16 in HBM; tcgen05 products of bf16 activations with '
-                              'TF32-rounded weights, fp32 accumulate; fp32 master weights, statistics, GRU, optimizer)'}[args.precision],
+                      'bf16': 'bf16 (conv-stack activations + gradients stored as bf16 in HBM; tcgen05 kind::f16 bf16 x bf16 MMAs on the wide '
+                              'layers, one kind::tf32 pass on the narrow ones, fp32 accumulate; fp32 master weights, statistics, GRU, '
+                              'optimizer)'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': ('BASELINE configs[4] shape: ' if stream_mode else '') + workload_name(args, B),
                        'global_batch': gB, 'parallelism': f'dp{world}', 'precision': args.precision,
