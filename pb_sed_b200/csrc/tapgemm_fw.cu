@@ -44,6 +44,7 @@ struct FwParams {
   int t_tiles, f_chunks, items;
   unsigned w_bytes;
   int in_bf16, out_bf16;      // storage of `in` / of `out` and `ep_src` (bf16 activation maps)
+  int bfm;                    // 1: kind::f16 MMAs (bf16 operands, 8 channels per 16-byte chunk, all Cin channels in ONE stage)
   int nraw;                   // raw ring depth
   unsigned raw_stage;         // bytes of one raw strip: 130 frames x Cin elements (fp32 or bf16)
 };
@@ -86,6 +87,28 @@ fwprep_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_s
   }
 }
 
+// bf16 weight image (kind::f16): [dt 3][k-chunk Cin/8][n' = blk * Cout + n][8 bf16]
+__global__ void __launch_bounds__(256)
+fwprep_bf16_kernel(const float* __restrict__ W, long long w_tap_stride, long long w_sn, long long w_sc,
+                   int Cin, int Cout, int t00, int t01, int t02, int t10, int t11, int t12, int t20, int t21, int t22,
+                   __nv_bfloat16* __restrict__ img, double* __restrict__ rep, int rep_count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rep_count; i += gridDim.x * blockDim.x) rep[i] = 0.;
+  const int tapidx[3][3] = {{t00, t01, t02}, {t10, t11, t12}, {t20, t21, t22}};   // [df+1][dt+1]
+  const int nch = Cin / 8, N3 = 3 * Cout;
+  const int total = 3 * nch * N3 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int q = i >> 3;
+    const int np = q % N3; q /= N3;
+    const int kc = q % nch;
+    const int dt = q / nch;
+    const int blk = np / Cout, n = np - blk * Cout;
+    const int tap = tapidx[2 - blk][dt];
+    const int cin = kc * 8 + e;
+    img[i] = __float2bfloat16_rn(__ldg(W + (long long)tap * w_tap_stride + (long long)n * w_sn + (long long)cin * w_sc));
+  }
+}
+
 __global__ void __launch_bounds__(FW_THREADS, 1)
 tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int* __restrict__ seq_len,
@@ -104,7 +127,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
 
   if (tid == 0) {
     for (int i = 0; i < p.nraw; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], 128); }
-    const uint32_t n_issuers = p.single ? 1u : 3u;
+    const uint32_t n_issuers = (p.single || p.bfm) ? 1u : 3u;
     for (int i = 0; i < FW_NA; ++i) { mbar_init(&ctl->a_full[i], 128); mbar_init(&ctl->a_empty[i], n_issuers); }
     for (int h = 0; h < 2; ++h) {
       for (int i = 0; i < FW_MAXR; ++i) mbar_init(&ctl->acc_full[h][i], n_issuers);
@@ -147,6 +170,44 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
         const int rs = sit % p.nraw;
         const uint8_t* raw = r_smem + rs * p.raw_stage;
         mbar_wait(&ctl->raw_full[rs], (sit / p.nraw) & 1);             // the raw strip has landed
+        if (p.bfm) {
+          // bf16 operands: the whole strip (Cin = 16 / 32 channels = 2 / 4 chunks of 8) is ONE stage
+          const int nch = p.Cin >> 3, cb = tid % nch, rb = tid / nch, rstep = 128 / nch;
+          float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0, h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+          if (scale) {
+            s0 = __ldg(reinterpret_cast<const float4*>(scale + cb * 8)); s1 = __ldg(reinterpret_cast<const float4*>(scale + cb * 8 + 4));
+            h0 = __ldg(reinterpret_cast<const float4*>(shift + cb * 8)); h1 = __ldg(reinterpret_cast<const float4*>(shift + cb * 8 + 4));
+          }
+          const int slot = it % FW_NA;
+          uint8_t* img = a_smem + slot * FW_A_STAGE;
+          mbar_wait(&ctl->a_empty[slot], ((it / FW_NA) & 1) ^ 1);
+          for (int r = rb; r < FW_ROWS; r += rstep) {
+            const int t = t0 + r - 1;
+            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+            if (t >= 0 && t < len_in) {
+              o4 = *reinterpret_cast<const uint4*>(raw + 2 * (uint32_t)(r * p.Cin + cb * 8));
+              if (scale || p.relu) {
+                float4 x0 = bf16x4_to_float4(make_uint2(o4.x, o4.y)), x1 = bf16x4_to_float4(make_uint2(o4.z, o4.w));
+                if (scale) {
+                  x0.x = fmaf(x0.x, s0.x, h0.x); x0.y = fmaf(x0.y, s0.y, h0.y); x0.z = fmaf(x0.z, s0.z, h0.z); x0.w = fmaf(x0.w, s0.w, h0.w);
+                  x1.x = fmaf(x1.x, s1.x, h1.x); x1.y = fmaf(x1.y, s1.y, h1.y); x1.z = fmaf(x1.z, s1.z, h1.z); x1.w = fmaf(x1.w, s1.w, h1.w);
+                }
+                if (p.relu) {
+                  x0.x = fmaxf(x0.x, 0.f); x0.y = fmaxf(x0.y, 0.f); x0.z = fmaxf(x0.z, 0.f); x0.w = fmaxf(x0.w, 0.f);
+                  x1.x = fmaxf(x1.x, 0.f); x1.y = fmaxf(x1.y, 0.f); x1.z = fmaxf(x1.z, 0.f); x1.w = fmaxf(x1.w, 0.f);
+                }
+                const uint2 lo2 = float4_to_bf16x4(x0), hi2 = float4_to_bf16x4(x1);
+                o4 = make_uint4(lo2.x, lo2.y, hi2.x, hi2.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(img + (uint32_t)(cb * FW_ROWS + r) * 16) = o4;
+          }
+          fence_async_smem();
+          mbar_arrive(&ctl->a_full[slot]);
+          ++it;
+          mbar_arrive(&ctl->raw_empty[rs]);
+          continue;
+        }
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (scale) {
@@ -299,7 +360,7 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
     // The three passes of the split (hi*hi, lo*hi, hi*lo) are therefore issued by THREE threads in three warps,
     // each with fixed operand images; accumulation order is irrelevant, every barrier counts all issuers.
     const int pass = warp == 8 ? 0 : warp - 13;               // 0: hi*hi, 1: lo*hi, 2: hi*lo
-    if (lane == 0 && (pass == 0 || !p.single)) {
+    if (lane == 0 && (pass == 0 || !(p.single || p.bfm))) {
       uint32_t idesc[4];
       for (int n = 1; n <= 3; ++n) idesc[n] = make_idesc_tf32(FW_TM, n * Cout);
       const uint32_t W_LBO = (uint32_t)(3 * Cout) * 16, W_PART = FW_KCH * W_LBO;
@@ -322,6 +383,15 @@ tapgemm_fw_kernel(FwParams p, const float* __restrict__ in, const float* __restr
             mbar_wait(&ctl->a_full[slot], (it / FW_NA) & 1);
             tc_fence_after();
             const uint32_t a_hi = a_base + slot * FW_A_STAGE, a_lo = a_hi + FW_A_PART;
+            if (p.bfm) {                 // kind::f16: K = 16 = two 8-channel chunks per instruction, one pass
+              const uint32_t nch = (uint32_t)p.Cin >> 3, idb = make_idesc_bf16(FW_TM, nblk * Cout);
+              for (uint32_t dt = 0; dt < 3; ++dt)
+                for (uint32_t ks = 0; ks < nch / 2; ++ks)
+                  mma_bf16(d, desc_at(a_d0, a_hi + dt * 16 + (ks * 2) * FW_A_LBO),
+                           desc_at(w_d0, w_base + (dt * nch + ks * 2) * W_LBO + (uint32_t)(blk0 * Cout) * 16), idb, 1u);
+              mma_commit(&ctl->a_empty[slot]);
+              continue;
+            }
             const uint32_t w_kb = w_base + (uint32_t)(kb * 2) * W_PART + (uint32_t)(blk0 * Cout) * 16;
             const uint32_t id = idesc[nblk];
 #pragma unroll
@@ -418,7 +488,10 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   const long long rows = (long long)p.B * p.F * p.T;
   if (items > (1 << 30) || rows >= (1LL << 31) - 256) return 0;
   p.items = (int)items;
-  p.w_bytes = 3u * p.nkb * 2u * FW_KCH * (3u * p.Cout) * 16u;
+  static const int use_bfm = getenv("PBSED_BF16_MMA") ? atoi(getenv("PBSED_BF16_MMA")) : 1;
+  p.bfm = use_bfm && d->in_dtype == PBSED_BF16 && d->precision == 3;
+  if (p.bfm) p.nkb = 1;
+  p.w_bytes = p.bfm ? 3u * (p.Cin / 8) * (3u * p.Cout) * 16u : 3u * p.nkb * 2u * FW_KCH * (3u * p.Cout) * 16u;
   const bool want_sums = out_stats || ep_sums;
   const long long rep_bytes = (long long)FW_STAT_REP * p.Cout * 2 * sizeof(double);
   if ((long long)p.w_bytes + 256 + (want_sums ? rep_bytes : 0) > ws_bytes) return 0;
@@ -430,6 +503,11 @@ int tapgemm_fw_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
   p.raw_stage = (unsigned)FW_ROWS * p.Cin * 4;                    // sized for fp32; bf16 strips use half of it
   p.nraw = FW_NRAW * FW_KB / p.Cin;
   float* img = reinterpret_cast<float*>(workspace);
+  if (p.bfm)
+    fwprep_bf16_kernel<<<cdiv(p.w_bytes / 2, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,
+        tapidx[0][0], tapidx[0][1], tapidx[0][2], tapidx[1][0], tapidx[1][1], tapidx[1][2],
+        tapidx[2][0], tapidx[2][1], tapidx[2][2], reinterpret_cast<__nv_bfloat16*>(img), rep, want_sums ? FW_STAT_REP * p.Cout * 2 : 0);
+  else
   fwprep_kernel<<<cdiv(p.w_bytes / 8, 256), 256, 0, st>>>(W, d->w_tap_stride, d->w_sn, d->w_sc, p.Cin, p.Cout,
       tapidx[0][0], tapidx[0][1], tapidx[0][2], tapidx[1][0], tapidx[1][1], tapidx[1][2],
       tapidx[2][0], tapidx[2][1], tapidx[2][2], img, p.single, rep, want_sums ? FW_STAT_REP * p.Cout * 2 : 0);
