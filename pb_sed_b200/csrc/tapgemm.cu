@@ -422,6 +422,9 @@ static int launch_wgrad(const TapParams& p, const float* in, const float* scale,
 int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                               const float* shift, const int* seq_len, const float* dout,
                               int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled);
+int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                                 const float* shift, const int* seq_len, const float* dout,
+                                 int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled);
 int wgrad_mma_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale, const float* shift,
                        const int* seq_len, const float* dout, int mask_out, float* dW, float* dbias,
                        cudaStream_t st, int* handled);
@@ -438,6 +441,8 @@ extern "C" int pbsed_tapgemm_wgrad(const pbsed_tapgemm_desc* d, const float* in,
   {
     int handled = 0;
     rc = conv_cin1_wgrad_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
+    if (handled || rc) return rc;
+    rc = tapgemm_wgrad_stack_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
     if (handled || rc) return rc;
     rc = wgrad_mma_dispatch(d, in, scale, shift, seq_len, dout, mask_out, dW, dbias, st, &handled);
     if (handled || rc) return rc;

@@ -536,6 +536,10 @@ struct WgParams {
   int row_splits;
   int single;            // 1: one TF32 pass (precision 3)
   int in_bf16, out_bf16; // storage of `in` / `dout` (bf16 activation maps; wgrad_tma_kernel only)
+  // row-stacked mode of wgrad_tma_kernel (narrow 3x3 layers): stk_rz dout rows / stk_rz + 2 input rows of one clip
+  // act as Ms = (virtual rows) * Cz / Nc = (virtual rows) * Cx "channels" of ONE 128-lane tile
+  int stk, stk_rz, stk_groups, Cz, Cx;
+  int tap_of[9];         // (df + 1) * 3 + (dt + 1) -> index of that tap in the caller's table
 };
 
 struct __align__(16) WgCtl {
@@ -827,6 +831,69 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
 }
 
 
+// ---- accumulator (TMEM) -> dW, shared by wgrad_tma_kernel and wgrad_bf16_kernel.
+// Every CTA adds its partial sums into the same dW with global reductions, and measured (r02, 148 CTAs x 128 lanes x
+// 384 columns = 7 M scalar atomics on <= 50 k addresses) that epilogue was 70 - 100 us of a 0.25 - 0.35 ms launch.
+// TMEM column ci of a tap holds input channel 4 * (ci % aq) + ci / aq (quad-major operand rows), so the columns
+// cb + {0, aq, 2 aq, 3 aq} are four CONSECUTIVE channels: one 16-byte `red.global.add.v4.f32` instead of four.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void wg_epilogue(const WgParams& p, uint32_t tmem_base, int warp, int lane, int g, int ntap,
+                                            int m0, int c0, int zq, int aq, float* __restrict__ dW) {
+  const int lw = warp & 3, half = warp >> 2;              // TMEM lane quarter / column half
+  const int m = lw * 32 + lane;                            // operand row -> channel (quad-major)
+  const int n = m0 + 4 * (m % zq) + m / zq;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(lw * 32) << 16);
+  const bool vec = p.w_sc == 1 && aq >= 16 && (((uintptr_t)dW) & 15) == 0 && p.w_tap_stride % 4 == 0 && p.w_sn % 4 == 0;
+  if (vec) {
+    // stacked: block (dout row rzv, input row rx) is the tap df = rx - 1 - rzv
+    const int rzv = p.stk ? n / p.Cz : 0, co = p.stk ? n % p.Cz : n;
+    const bool row_ok = m < p.Ms && (!p.stk || rzv < p.stk_rz);
+    for (int j = 0; j < ntap; ++j) {
+      const int dt = p.g_dt[g][j];
+      float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn + c0;
+      for (int cb = half * 16; cb < aq; cb += 32) {
+        float v[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld16(lane_base + (uint32_t)(j * p.Nc + q * aq + cb), v[q]);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (v[0][k] == 0.f && v[1][k] == 0.f && v[2][k] == 0.f && v[3][k] == 0.f) continue;
+          const int c = 4 * (cb + k);
+          if (p.stk) {
+            const int ddf = c / p.Cx - 1 - rzv;
+            if (ddf < -1 || ddf > 1) continue;
+            red_add_v4(dW + (long long)p.tap_of[(ddf + 1) * 3 + dt + 1] * p.w_tap_stride + (long long)co * p.w_sn + c % p.Cx,
+                       v[0][k], v[1][k], v[2][k], v[3][k]);
+          } else {
+            red_add_v4(dst + c, v[0][k], v[1][k], v[2][k], v[3][k]);
+          }
+        }
+      }
+    }
+    return;
+  }
+  if (p.stk) return;                                       // (the stacked dispatch guarantees the vector path)
+  for (int j = 0; j < ntap; ++j) {
+    float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
+    for (int cc = half * 16; cc < p.Nc; cc += 32) {
+      float v[16];
+      tmem_ld16(lane_base + (uint32_t)(j * p.Nc + cc), v);
+      if (m < p.Ms) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int ci = cc + k;
+          const int c = c0 + 4 * (ci % aq) + ci / aq;
+          if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
+        }
+      }
+    }
+  }
+}
+
 // =====================================================================================
 // wgrad_tma_kernel: the same tensor-core weight gradient, with the global loads taken OFF the producers'
 // critical path.  A loader thread streams RAW fp32 tiles -- dout [32 frames x Ms channels] and the layer input
@@ -842,16 +909,18 @@ wgrad_tc_kernel(WgParams p, const float* __restrict__ in, const float* __restric
 constexpr int WG_RAW_MAX = 6;
 constexpr int WG_RAW_AROWS = WG_KR + 2;
 
+constexpr int WT_Z = 256, WT_A = 320, WT_CONV = WT_Z + WT_A;     // wgrad_tma_kernel: dout / input converter threads
+
 struct __align__(16) WgTmaCtl {
   uint64_t full[WG_STAGES], empty[WG_STAGES], raw_full[WG_RAW_MAX], raw_empty[WG_RAW_MAX], acc_full;
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(WG_PROD + 64)
+__global__ void __launch_bounds__(WT_CONV + 64)
 wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_a,
-                 int raw_stages, const float* __restrict__ scale, const float* __restrict__ shift,
-                 const int* __restrict__ seq_len, const float* __restrict__ dout, float* __restrict__ dW,
-                 float* __restrict__ dbias) {
+                 int raw_stages, const float* __restrict__ in_raw, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const int* __restrict__ seq_len, const float* __restrict__ dout,
+                 float* __restrict__ dW, float* __restrict__ dbias) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int zq = p.Ms / 4, aq = p.Nc / 4;           // channel quads per operand
   const uint32_t Z_LBO = 128 * 16, A_LBO = (uint32_t)p.Nc * 16;
@@ -868,24 +937,25 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
   const int m0 = m_slice * p.Ms, c0 = c_slice * p.Nc;
   const int df = p.g_df[g], ntap = p.g_n[g];
   const int t_blocks = (p.T + WG_TB - 1) / WG_TB;
-  const int total_units = p.B * p.F_out * t_blocks;
+  const int FO = p.stk ? p.stk_groups : p.F_out;     // row groups when stacked
+  const int total_units = p.B * FO * t_blocks;
   const bool do_bias = dbias != nullptr && g == 0 && c_slice == 0;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < ntap * p.Nc) tmem_cols <<= 1;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&ctl->full[i], WG_PROD); mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < raw_stages; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], WG_PROD); }
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&ctl->full[i], WT_CONV); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < raw_stages; ++i) { mbar_init(&ctl->raw_full[i], 1); mbar_init(&ctl->raw_empty[i], WT_CONV); }
     mbar_init(&ctl->acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == WG_PROD / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
+  if (warp == WT_CONV / 32) tmem_alloc(&ctl->tmem_base, tmem_cols);
   if (p.Ms < 128) {      // operand rows m >= Ms are read by the M = 128 MMA but never produced: zero once
     for (int s = 0; s < WG_STAGES; ++s)
       for (int part = 0; part < 2; ++part)
         for (int ch = 0; ch < WG_ZCH; ++ch) {
           float4* base = reinterpret_cast<float4*>(smem_raw + s * STAGE + part * Z_PART + ch * Z_LBO);
-          for (int i = p.Ms + tid; i < 128; i += WG_PROD + 64) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = p.Ms + tid; i < 128; i += WT_CONV + 64) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     fence_async_smem();
   }
@@ -894,23 +964,37 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp < WG_PROD / 32) {
+  if (warp < WT_CONV / 32) {
     // ============================== converters ==============================
+    // warps 0-7 convert the dout tile (and run the epilogue), warps 8-17 the input tile: with 8 chunks x 32 quads
+    // and 10 x 32 every thread owns ONE 4-frame x 4-channel block per stage (r02: eight converter warps doing
+    // both tiles needed 2.5 us per stage, latency bound at 2 warps per scheduler, against 2.1 us of MMAs)
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int zqi = tid % zq, aqi = tid % aq;
-    const int zj0 = tid / zq, zjs = WG_PROD / zq, aj0 = tid / aq, ajs = WG_PROD / aq;
+    const bool do_z = tid < WT_Z;
+    const int lt = do_z ? tid : tid - WT_Z;
+    const int zqi = lt % zq, aqi = lt % aq;
+    const int zj0 = do_z ? lt / zq : WG_ZCH, zjs = WT_Z / zq, aj0 = do_z ? WG_ACH : lt / aq, ajs = WT_A / aq;
+    // raw tile addressing: [frame][channel] as the tensor-map box lands it, or (stacked) [row][frame][channel]
+    const int cqz = p.stk ? p.Cz / 4 : zq, cqa = p.stk ? p.Cx / 4 : aq;
+    const int zrow_v = zqi / cqz, arow_v = aqi / cqa;                 // virtual row of this thread's channel quad
+    const uint32_t z_e0 = p.stk ? (uint32_t)(zrow_v * WG_KR * p.Cz + (zqi % cqz) * 4) : (uint32_t)(zqi * 4);
+    const uint32_t a_e0 = p.stk ? (uint32_t)(arow_v * WG_RAW_AROWS * p.Cx + (aqi % cqa) * 4) : (uint32_t)(aqi * 4);
+    const uint32_t z_rs = p.stk ? p.Cz : p.Ms, a_rs = p.stk ? p.Cx : p.Nc;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     int it = 0;
     for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
       const int tb = u % t_blocks, gq = u / t_blocks;
-      const int fo = gq % p.F_out, b = gq / p.F_out;
+      const int fo = gq % FO, b = gq / FO;
       const int f_src = fo + df;
-      const bool f_ok = f_src >= 0 && f_src < p.F_in;
+      const bool f_ok = p.stk || (f_src >= 0 && f_src < p.F_in);
       if (!f_ok && !do_bias) continue;
+      // stacked: dout rows fo * rz + [0, rz), input rows fo * rz - 1 + [0, rz + 2); the others read as zero
+      const bool z_row_ok = !p.stk || (zrow_v < p.stk_rz && fo * p.stk_rz + zrow_v < p.F_out);
+      const bool a_row_ok = !p.stk || (arow_v < p.stk_rz + 2 && (unsigned)(fo * p.stk_rz - 1 + arow_v) < (unsigned)p.F_in);
       const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
       const int len_out = p.mask_out ? len_b : p.T;
       const int t_end = min(p.T, (tb + 1) * WG_TB);
-      if (!f_ok) {                                 // bias-only visit of a border row group: plain loads
+      if (!f_ok) {                                 // bias-only visit of a border row group: plain loads (dout warps)
         const long long zsrc = ((long long)b * p.F_out + fo) * p.T * p.out_stride + m0 + zqi * 4;
         for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR)
           for (int j = zj0; j < WG_ZCH; j += zjs)
@@ -924,8 +1008,8 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
             }
         continue;
       }
-      if (scale) {
-        const int aff = (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
+      if (scale && !do_z) {
+        const int aff = p.stk ? (aqi % cqa) * 4 : (p.per_f ? f_src * p.Cin : 0) + c0 + aqi * 4;
         sc = __ldg(reinterpret_cast<const float4*>(scale + aff));
         sh = __ldg(reinterpret_cast<const float4*>(shift + aff));
       }
@@ -944,9 +1028,9 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = j + 8 * i;
-            const uint32_t e = (uint32_t)(r * p.Ms + zqi * 4);
+            const uint32_t e = z_e0 + (uint32_t)r * z_rs;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t0 + r < len_out)
+            if (z_row_ok && t0 + r < len_out)
               v[i] = p.out_bf16 ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(rz + 2 * e))
                                 : *reinterpret_cast<const float4*>(rz + 4 * e);
           }
@@ -966,8 +1050,8 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
           for (int i = 0; i < 4; ++i) {
             const int r = jj + 8 * i, t = t0 + r - 1;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t >= 0 && t < len_b) {
-              const uint32_t e = (uint32_t)(r * p.Nc + aqi * 4);
+            if (a_row_ok && t >= 0 && t < len_b) {
+              const uint32_t e = a_e0 + (uint32_t)r * a_rs;
               x = p.in_bf16 ? bf16x4_to_float4(*reinterpret_cast<const uint2*>(ra + 2 * e))
                             : *reinterpret_cast<const float4*>(ra + 4 * e);
               if (scale) {
@@ -989,38 +1073,20 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
         mbar_arrive(&ctl->full[slot]);
       }
     }
-    if (do_bias) {
-      float* db = dbias + m0 + zqi * 4;
+    if (do_bias && do_z) {
+      float* db = dbias + (p.stk ? (zqi % cqz) * 4 : m0 + zqi * 4);
       if (bsum.x != 0.f) atomicAdd(db + 0, bsum.x);
       if (bsum.y != 0.f) atomicAdd(db + 1, bsum.y);
       if (bsum.z != 0.f) atomicAdd(db + 2, bsum.z);
       if (bsum.w != 0.f) atomicAdd(db + 3, bsum.w);
     }
     // ============================== epilogue ==============================
+    if (!do_z) goto done;
     mbar_wait(&ctl->acc_full, 0);
     tc_fence_after();
-    const int lw = warp & 3, half = warp >> 2;              // TMEM lane quarter / column half
-    const int m = lw * 32 + lane;                            // operand row -> channel (quad-major)
-    const int n = m0 + 4 * (m % zq) + m / zq;
-    if (it > 0) {                                            // no MMA issued -> TMEM is uninitialised
-      for (int j = 0; j < ntap; ++j) {
-        float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
-        for (int cc = half * 16; cc < p.Nc; cc += 32) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
-          if (m < p.Ms) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int ci = cc + k;
-              const int c = c0 + 4 * (ci % aq) + ci / aq;
-              if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
-            }
-          }
-        }
-      }
-    }
+    if (it > 0) wg_epilogue(p, tmem_base, warp, lane, g, ntap, m0, c0, zq, aq, dW);   // no MMA issued -> TMEM is uninitialised
     tc_fence_before();
-  } else if (warp == WG_PROD / 32) {
+  } else if (warp == WT_CONV / 32) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, p.Nc);
@@ -1028,9 +1094,9 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       int it = 0;
       for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
         const int tb = u % t_blocks, gq = u / t_blocks;
-        const int fo = gq % p.F_out;
+        const int fo = gq % FO;
         const int f_src = fo + df;
-        if (f_src < 0 || f_src >= p.F_in) continue;
+        if (!p.stk && (f_src < 0 || f_src >= p.F_in)) continue;
         const int t_end = min(p.T, (tb + 1) * WG_TB);
         for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR) {
           const int slot = it % WG_STAGES;
@@ -1064,10 +1130,37 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       int it = 0;
       for (int u = blockIdx.x; u < total_units; u += p.row_splits) {
         const int tb = u % t_blocks, gq = u / t_blocks;
-        const int fo = gq % p.F_out, b = gq / p.F_out;
+        const int fo = gq % FO, b = gq / FO;
         const int f_src = fo + df;
-        if (f_src < 0 || f_src >= p.F_in) continue;
+        if (!p.stk && (f_src < 0 || f_src >= p.F_in)) continue;
         const int t_end = min(p.T, (tb + 1) * WG_TB);
+        if (p.stk) {
+          // stacked: one contiguous run of frames per map row (1-D bulk copies; rows of 16 / 32 channels are too
+          // short for efficient tensor-map boxes).  Frames outside [0, T) are not copied -- the converters select
+          // by frame index -- and rows outside the map are skipped (the converters zero them).
+          const uint32_t ez = p.out_bf16 ? 2u : 4u, ea = p.in_bf16 ? 2u : 4u;
+          const int f0 = fo * p.stk_rz;
+          int nzr = p.F_out - f0; if (nzr > p.stk_rz) nzr = p.stk_rz;
+          const int a_lo = f0 - 1 < 0 ? 0 : f0 - 1, a_hi = f0 + p.stk_rz < p.F_in - 1 ? f0 + p.stk_rz : p.F_in - 1;
+          for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
+            const int rs = it % raw_stages;
+            mbar_wait(&ctl->raw_empty[rs], ((it / raw_stages) & 1) ^ 1);
+            uint8_t* dst = raw_base + (uint32_t)rs * RAW;
+            const int nz = min(WG_KR, p.T - t0);
+            const int ts = t0 - 1 < 0 ? 0 : t0 - 1, te = min(t0 + WG_KR + 1, p.T);
+            const uint32_t zb = (uint32_t)(nz * p.Cz) * ez, ab = (uint32_t)((te - ts) * p.Cx) * ea;
+            mbar_expect_tx(&ctl->raw_full[rs], zb * (uint32_t)nzr + ab * (uint32_t)(a_hi - a_lo + 1));
+            for (int r = 0; r < nzr; ++r)
+              bulk_g2s(dst + (uint32_t)(r * WG_KR * p.Cz) * ez,
+                       reinterpret_cast<const uint8_t*>(dout) + (((size_t)b * p.F_out + f0 + r) * p.T + t0) * p.Cz * ez,
+                       zb, &ctl->raw_full[rs]);
+            for (int f = a_lo; f <= a_hi; ++f)
+              bulk_g2s(dst + RAW_Z + (uint32_t)(((f - f0 + 1) * WG_RAW_AROWS + ts - (t0 - 1)) * p.Cx) * ea,
+                       reinterpret_cast<const uint8_t*>(in_raw) + (((size_t)b * p.F_in + f) * p.T + ts) * p.Cx * ea,
+                       ab, &ctl->raw_full[rs]);
+          }
+          continue;
+        }
         const int zrow = (b * p.F_out + fo) * p.T, arow = (b * p.F_in + f_src) * p.T;
         for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
           const int rs = it % raw_stages;
@@ -1080,8 +1173,9 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       }
     }
   }
+done:
   __syncthreads();
-  if (warp == WG_PROD / 32) {
+  if (warp == WT_CONV / 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -1254,26 +1348,7 @@ wgrad_bf16_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __
     // ============================== epilogue ==============================
     mbar_wait(&ctl->acc_full, 0);
     tc_fence_after();
-    const int lw = warp & 3, half = warp >> 2;
-    const int m = lw * 32 + lane;
-    const int n = m0 + 4 * (m % zq) + m / zq;
-    if (it > 0) {
-      for (int j = 0; j < ntap; ++j) {
-        float* dst = dW + (long long)p.g_tap[g][j] * p.w_tap_stride + (long long)n * p.w_sn;
-        for (int cc = half * 16; cc < p.Nc; cc += 32) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lw * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
-          if (m < p.Ms) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int ci = cc + k;
-              const int c = c0 + 4 * (ci % aq) + ci / aq;
-              if (v[k] != 0.f) atomicAdd(dst + (long long)c * p.w_sc, v[k]);
-            }
-          }
-        }
-      }
-    }
+    if (it > 0) wg_epilogue(p, tmem_base, warp, lane, g, ntap, m0, c0, zq, aq, dW);
     tc_fence_before();
   } else if (warp == WG_PROD / 32) {
     // ============================== MMA issuer ==============================
@@ -1462,6 +1537,65 @@ int tapgemm_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const floa
 
 
 
+// Row-stacked weight gradient of the narrow 3x3 layers (16 / 32 channels on the input side).  One dout row x one
+// input row is a 16..64 x 16..32 product -- far below a 128-lane tile, and tcgen05.mma costs ~115 cycles however
+// small it is -- so SEVERAL frequency rows of a clip are presented to wgrad_tma_kernel as channels of one tile:
+// M = rz dout rows x Cout, N = (rz + 2) input rows x Cin (padded to 128 virtual channels).  Block (row i, row j) of
+// the accumulator is the tap df = j - 1 - i; the time taps stay descriptor offsets.  A third to a half of each
+// MMA is padding, but there are rz x 3 fewer of them than tile-per-row would need.
+int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
+                                 const float* shift, const int* seq_len, const float* dout,
+                                 int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
+  *handled = 0;
+  static const int use_stack = getenv("PBSED_WG_STACK") ? atoi(getenv("PBSED_WG_STACK")) : 1;
+  if (!use_stack || (d->precision != 1 && d->precision != 3)) return 0;
+  if (d->ntaps != 9 || d->F_in != d->F_out || d->per_f) return 0;
+  int rz, ms, nc;
+  if (d->Cout == 16 && d->Cin == 16)      { rz = 6; ms = 128; nc = 128; }
+  else if (d->Cout == 32 && d->Cin == 16) { rz = 4; ms = 128; nc = 128; }
+  else if (d->Cout == 32 && d->Cin == 32) { rz = 2; ms = 64;  nc = 128; }
+  else if (d->Cout == 64 && d->Cin == 32) { rz = 2; ms = 128; nc = 128; }
+  else return 0;
+  if ((d->in_stride > 0 && d->in_stride != d->Cin) || (d->out_stride > 0 && d->out_stride != d->Cout)) return 0;
+  if ((((uintptr_t)in | (uintptr_t)dout | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return 0;
+  WgParams p = {};
+  for (int i = 0; i < 9; ++i) p.tap_of[i] = -1;
+  for (int i = 0; i < 9; ++i) {
+    if (d->df[i] < -1 || d->df[i] > 1 || d->dt[i] < -1 || d->dt[i] > 1) return 0;
+    p.tap_of[(d->df[i] + 1) * 3 + d->dt[i] + 1] = i;
+  }
+  for (int i = 0; i < 9; ++i) if (p.tap_of[i] < 0) return 0;
+  p.B = d->B; p.F_in = d->F_in; p.F_out = d->F_out; p.T = d->T; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.relu = d->relu; p.per_f = 0; p.mask_out = mask_out;
+  p.in_stride = d->Cin; p.out_stride = d->Cout;
+  p.w_tap_stride = d->w_tap_stride; p.w_sn = d->w_sn; p.w_sc = d->w_sc;
+  p.single = d->precision == 3;
+  p.in_bf16 = d->in_dtype == PBSED_BF16; p.out_bf16 = d->out_dtype == PBSED_BF16;
+  p.Ms = ms; p.Nc = nc; p.m_slices = 1; p.c_slices = 1;
+  p.ngroups = 1; p.g_df[0] = 0; p.g_n[0] = 3;
+  for (int j = 0; j < 3; ++j) { p.g_tap[0][j] = j; p.g_dt[0][j] = j - 1; }
+  p.stk = 1; p.stk_rz = rz; p.stk_groups = cdiv(d->F_out, rz); p.Cz = d->Cout; p.Cx = d->Cin;
+  if ((long long)p.B * p.stk_groups * cdiv(p.T, WG_TB) > 0x7fffffffLL) return 0;
+  const size_t stage = 2 * (size_t)WG_ZCH * 128 * 16 + 2 * (size_t)WG_ACH * p.Nc * 16;
+  const size_t raw = (size_t)WG_KR * p.Ms * (p.out_bf16 ? 2 : 4) + (size_t)WG_RAW_AROWS * p.Nc * (p.in_bf16 ? 2 : 4);
+  const size_t budget = 227 * 1024 - WG_STAGES * stage - sizeof(WgTmaCtl) - 256;
+  int raw_stages = (int)(budget / raw);
+  if (raw_stages > WG_RAW_MAX) raw_stages = WG_RAW_MAX;
+  if (raw_stages < 2) return 0;
+  const int units = p.B * p.stk_groups * cdiv(p.T, WG_TB);
+  int rs = 148;
+  if (rs > units) rs = units;
+  p.row_splits = rs;
+  const size_t smem = WG_STAGES * stage + (size_t)raw_stages * raw + sizeof(WgTmaCtl) + 128;
+  cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  CUtensorMap none = {};
+  pbsed_note_kernel("wgrad_tma_kernel[rows]");
+  wgrad_tma_kernel<<<dim3(rs, 1, 1), WT_CONV + 64, smem, st>>>(p, none, none, raw_stages, in, scale, shift, seq_len, dout, dW, dbias);
+  *handled = 1;
+  return pbsed_after_launch();
+}
+
 int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, const float* scale,
                               const float* shift, const int* seq_len, const float* dout,
                               int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
@@ -1528,7 +1662,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
     int raw_stages = (int)(budget / raw);
     if (raw_stages > WG_RAW_MAX) raw_stages = WG_RAW_MAX;
     CUtensorMap tm_z, tm_a;
-    if (raw_stages >= 2 &&
+    if (raw_stages >= 2 && WT_A % (p.Nc / 4) == 0 &&
         make_tmap_2d(&tm_z, dout, p.Cout, rows_z, p.out_stride, p.Ms, WG_KR, p.out_bf16) &&
         make_tmap_2d(&tm_a, in, p.Cin, rows_a, p.in_stride, p.Nc, WG_RAW_AROWS, p.in_bf16)) {
       int rs = 148 / roles;                            // one CTA per SM: a single wave, deep prefetch instead of co-residency
@@ -1540,7 +1674,7 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
       if (e != cudaSuccess) return (int)e;
       dim3 grid(rs, p.ngroups, p.m_slices * p.c_slices);
       pbsed_note_kernel("wgrad_tma_kernel");
-      wgrad_tma_kernel<<<grid, WG_PROD + 64, smem, st>>>(p, tm_z, tm_a, raw_stages, scale, shift, seq_len, dout, dW, dbias);
+      wgrad_tma_kernel<<<grid, WT_CONV + 64, smem, st>>>(p, tm_z, tm_a, raw_stages, in, scale, shift, seq_len, dout, dW, dbias);
       *handled = 1;
       return pbsed_after_launch();
     }

@@ -88,6 +88,9 @@ def test_tc_dgrad_with_relu_mask_epilogue(built_lib):
 
 @pytest.mark.parametrize('B,F,T,Cin,Cout,taps,relu', [
     (2, 3, 37, 16, 16, TAPS_3x3, True),
+    (3, 13, 45, 16, 16, TAPS_3x3, False),      # narrow layers: row-stacked tiles with a ragged last row group
+    (2, 7, 100, 16, 32, TAPS_3x3, True),
+    (3, 5, 70, 32, 32, TAPS_3x3, True),
     (2, 4, 500, 32, 64, TAPS_3x3, True),
     (2, 2, 300, 128, 256, TAPS_3x3, True),
     (3, 1, 500, 256, 768, TAPS_1x1, False),

@@ -125,6 +125,16 @@ def stalls(path, pattern='.', skip=0):
     top = sorted(((int(r[A]), i, r[S].strip()) for i, r in enumerate(body) if len(r) > A and r[A].isdigit()), reverse=True)[:14]
     for n, i, src in top:
         print(f'   {100 * n / max(tot, 1):5.1f}%  #{i:5d}  {src[:110]}')
+    # synchronisation sites: samples of each mbarrier wait / barrier / tensor-core / bulk-copy / reduction instruction
+    # together with the 5 instructions after it (the polling loop's branch), so "who waits for whom" can be read off
+    print('   -- synchronisation / async sites (instruction + following 5):')
+    smp = [int(r[A]) if len(r) > A and r[A].isdigit() else 0 for r in body]
+    for i, r in enumerate(body):
+        src = r[S].strip() if len(r) > S else ''
+        if re.search(r'SYNCS\.PHASECHK|BAR\.SYNC|UTCHMMA|UBLKCP|UTMALDG|REDG|LDTM|UTCBAR', src):
+            w = sum(smp[i:i + 6])
+            if w > .003 * tot:
+                print(f'   {100 * w / max(tot, 1):5.1f}%  #{i:5d}  {src[:100]}')
 
 
 if __name__ == '__main__':
