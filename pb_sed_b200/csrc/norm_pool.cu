@@ -474,36 +474,45 @@ maxpool_f_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ i
 // the same channel quad for its whole loop and the sums live in registers until the end.
 template <bool STATS>
 __global__ void __launch_bounds__(256)
-maxpool2_f4_kernel(const void* __restrict__ x, int Fo, long long TC4, void* __restrict__ y,
-                   uchar4* __restrict__ idx, long long total4, int C4, const int* __restrict__ seq_len,
+maxpool2_f4_kernel(const void* __restrict__ x, int Fo, int TC4, void* __restrict__ y,
+                   uchar4* __restrict__ idx, int rows, int C4, const int* __restrict__ seq_len,
                    double* __restrict__ stats, int bf_in, int bf_out) {
+  // grid (gx, gy): blockIdx.y strides over the pooled rows gq = b * Fo + fo, blockIdx.x * 256 + tid over the row's
+  // T * C / 4 quads -- 32-bit index arithmetic, no division in the inner loop, two row pairs in flight per thread
+  // (r02: the flat 64-bit-indexed version ran at 2.3 TB/s, instruction bound)
   __shared__ float red[2][1024];
-  const long long stride = (long long)gridDim.x * blockDim.x;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
-    const long long tc = i % TC4, gq = i / TC4;         // gq = b * Fo + fo
-    const float4 a = ld_act4(x, 4 * ((2 * gq) * TC4 + tc), bf_in), c = ld_act4(x, 4 * ((2 * gq + 1) * TC4 + tc), bf_in);
+  const int tc0 = blockIdx.x * 256 + threadIdx.x, tstep = gridDim.x * 256;
+  auto pool1 = [&](const float4 a, const float4 c, long long o, bool valid) {
     float4 r; uchar4 k;
     k.x = (c.x > a.x || c.x != c.x) ? 1 : 0; r.x = k.x ? c.x : a.x;
     k.y = (c.y > a.y || c.y != c.y) ? 1 : 0; r.y = k.y ? c.y : a.y;
     k.z = (c.z > a.z || c.z != c.z) ? 1 : 0; r.z = k.z ? c.z : a.z;
     k.w = (c.w > a.w || c.w != c.w) ? 1 : 0; r.w = k.w ? c.w : a.w;
-    st_act4(y, 4 * i, r, bf_out);
-    if (idx) idx[i] = k;
-    if (STATS) {
-      const int t = (int)(tc / C4);
-      const int b = (int)(gq / Fo);
-      if (!seq_len || t < __ldg(seq_len + b)) {
-        s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
-        ss.x = fmaf(r.x, r.x, ss.x); ss.y = fmaf(r.y, r.y, ss.y); ss.z = fmaf(r.z, r.z, ss.z); ss.w = fmaf(r.w, r.w, ss.w);
-      }
+    st_act4(y, 4 * o, r, bf_out);
+    if (idx) idx[o] = k;
+    if (STATS && valid) {
+      s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
+      ss.x = fmaf(r.x, r.x, ss.x); ss.y = fmaf(r.y, r.y, ss.y); ss.z = fmaf(r.z, r.z, ss.z); ss.w = fmaf(r.w, r.w, ss.w);
     }
+  };
+  for (int gq = blockIdx.y; gq < rows; gq += gridDim.y) {
+    const long long in0 = (long long)(2 * gq) * TC4, in1 = in0 + TC4, out0 = (long long)gq * TC4;
+    const int tc_valid = (STATS && seq_len) ? min(__ldg(seq_len + gq / Fo), TC4 / C4) * C4 : TC4;   // quads of valid frames
+    int tc = tc0;
+    for (; tc + tstep < TC4; tc += 2 * tstep) {
+      const float4 a0 = ld_act4(x, 4 * (in0 + tc), bf_in), c0 = ld_act4(x, 4 * (in1 + tc), bf_in);
+      const float4 a1 = ld_act4(x, 4 * (in0 + tc + tstep), bf_in), c1 = ld_act4(x, 4 * (in1 + tc + tstep), bf_in);
+      pool1(a0, c0, out0 + tc, tc < tc_valid);
+      pool1(a1, c1, out0 + tc + tstep, tc + tstep < tc_valid);
+    }
+    if (tc < TC4) pool1(ld_act4(x, 4 * (in0 + tc), bf_in), ld_act4(x, 4 * (in1 + tc), bf_in), out0 + tc, tc < tc_valid);
   }
   if (STATS) {
     const int C = 4 * C4;
     for (int j = threadIdx.x; j < C; j += 256) { red[0][j] = 0.f; red[1][j] = 0.f; }
     __syncthreads();
-    const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % C4);
+    const int q = tc0 % C4;                                 // 256 % C4 == 0: the quad is the same for every element of the thread
     atomicAdd(&red[0][4 * q + 0], s.x); atomicAdd(&red[0][4 * q + 1], s.y);
     atomicAdd(&red[0][4 * q + 2], s.z); atomicAdd(&red[0][4 * q + 3], s.w);
     atomicAdd(&red[1][4 * q + 0], ss.x); atomicAdd(&red[1][4 * q + 1], ss.y);
@@ -548,14 +557,19 @@ extern "C" int pbsed_maxpool_f(const float* x, int B, int F, int T, int C, int p
   const long long total = (long long)B * (F / pool) * T * C;
   if (pool == 2 && (F & 1) == 0 && (C & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)idx)) & 15) == 0) {
     const bool fused = out_stats && C <= 1024 && (256 % (C / 4)) == 0;
+    const long long tc4 = (long long)T * C / 4, rows = (long long)B * (F / 2);
+    if (tc4 > 0x7fffffffLL / 8 || rows > 0x7fffffffLL) return PBSED_EINVAL;
+    int gx = (int)((tc4 + 511) / 512);                     // two quads per thread and pass
+    if (gx > 8) gx = 8;
+    long long gy = (148 * 8 + gx - 1) / gx;
+    if (gy > rows) gy = rows;
+    const dim3 grid(gx, (unsigned)gy);
     if (fused)
-      maxpool2_f4_kernel<true><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
-          x, F / 2, (long long)T * C / 4, y,
-          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, seq_len, out_stats, in_dtype, out_dtype);
+      maxpool2_f4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          x, F / 2, (int)tc4, y, reinterpret_cast<uchar4*>(idx), (int)rows, C / 4, seq_len, out_stats, in_dtype, out_dtype);
     else
-      maxpool2_f4_kernel<false><<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(
-          x, F / 2, (long long)T * C / 4, y,
-          reinterpret_cast<uchar4*>(idx), total / 4, C / 4, nullptr, nullptr, in_dtype, out_dtype);
+      maxpool2_f4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          x, F / 2, (int)tc4, y, reinterpret_cast<uchar4*>(idx), (int)rows, C / 4, nullptr, nullptr, in_dtype, out_dtype);
     int rc = pbsed_after_launch();
     if (rc || fused || !out_stats) return rc;
     return pbsed_channel_stats(y, B, F / pool, T, C, 0, seq_len, out_stats, out_dtype, stream);

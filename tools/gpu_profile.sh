@@ -8,12 +8,15 @@ mkdir -p $O /tmp/rep
 python -c "import __graft_entry__ as g; g.build()" >/dev/null 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 500 -c 330 --csv --log-file $O/${TAG}_pipe_full_step.csv python tools/run_step.py 3 > /tmp/rep/ncu1.log 2>&1
 python tools/ncu_summary.py pipe $O/${TAG}_pipe_full_step.csv > $O/${TAG}_tensor_pipe_all_launches.txt
-cap() {  # name regex skip count
-  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o /tmp/rep/$1 python tools/run_step.py 2 > /tmp/rep/$1.log 2>&1
-  python tools/ncu_summary.py kernel /tmp/rep/$1.ncu-rep > $O/${TAG}_$1_ncu_full.txt 2>/dev/null
-  for sk in 0 $5; do python tools/ncu_summary.py stalls /tmp/rep/$1.ncu-rep "$2" $sk >> $O/${TAG}_$1_ncu_full.txt 2>/dev/null; done
+python tools/ncu_summary.py traffic $O/${TAG}_pipe_full_step.csv > $O/${TAG}_traffic.json && cp $O/${TAG}_traffic.json profiles/traffic.json   # bench.py below reads it
+cap() {  # name regex skip count [launch indices for the source-level stall view...]
+  local name=$1 re=$2 skip=$3 cnt=$4
+  shift 4
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$re" -s $skip -c $cnt -o /tmp/rep/$name python tools/run_step.py 2 > /tmp/rep/$name.log 2>&1
+  python tools/ncu_summary.py kernel /tmp/rep/$name.ncu-rep > $O/${TAG}_${name}_ncu_full.txt 2>/dev/null
+  for sk in 0 "$@"; do python tools/ncu_summary.py stalls /tmp/rep/$name.ncu-rep "$re" $sk >> $O/${TAG}_${name}_ncu_full.txt 2>/dev/null; done
 }
-cap wgrad_tma wgrad_tma_kernel 19 19 16
+cap wgrad_tma wgrad_tma_kernel 23 23 16 20
 cap tapgemm_fw tapgemm_fw_kernel 6 6 3
 cap tapgemm_tc tapgemm_tc_kernel 37 37 14
 cap gru "gru_(fwd|bwd)_kernel" 4 4 2

@@ -99,6 +99,39 @@ def pipe(path):
               f'{gemm_p / gemm_t:.1f} %')
 
 
+def traffic(path):
+    """profiles/traffic.json from the per-launch list of one eager step: measured DRAM bytes per launch of every kernel,
+    keyed by the name ``pbsed_last_kernel()`` reports (bench.py copies the dominant kernel's entry into roofline.traffic)."""
+    import json
+    lines = [l for l in open(path) if not l.startswith('==')]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if not row.get('Metric Name', '').startswith('dram__bytes'):
+            continue
+        try:
+            v = float(row['Metric Value'].replace(',', ''))
+        except ValueError:
+            continue
+        v *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(row.get('Metric Unit', ''), 1)
+        name = re.sub(r'\(.*', '', row['Kernel Name']).replace('void ', '').replace('<unnamed>::', '').strip()
+        m = re.match(r'(tapgemm_tc_kernel)<(\d+), (\d+), (\d+)', name)
+        if m:
+            name = '%s<%s,%s,%s>' % m.groups()
+        elif name.startswith(('wgrad_tma_kernel', 'wgrad_bf16_kernel', 'tapgemm_fw_kernel', 'wgrad_walk_kernel')):
+            name = name.split('<')[0]
+        d = per.setdefault(row['ID'], [name, 0.])
+        d[1] += v
+    agg = collections.OrderedDict()
+    for name, b in per.values():
+        a = agg.setdefault(name, [0, 0.])
+        a[0] += 1
+        a[1] += b
+    src = ('%s (ncu dram__bytes_read.sum + dram__bytes_write.sum of every launch of one eager B=32 train step, averaged '
+           'per kernel)' % path)
+    print(json.dumps({k: {'bytes_per_launch': a[1] / a[0], 'launches_captured': a[0], 'source': src}
+                      for k, a in agg.items() if a[1] / a[0] > 1e6}, indent=1))
+
+
 def stalls(path, pattern='.', skip=0):
     """source-level view of ONE launch of a --set full --import-source on capture: the most-sampled SASS
     instructions and the stall-reason totals (python tools/ncu_summary.py stalls X.ncu-rep <kernel regex> <skip>)."""
@@ -138,4 +171,4 @@ def stalls(path, pattern='.', skip=0):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'kernel': kernel, 'pipe': pipe, 'stalls': stalls}[sys.argv[1]](*sys.argv[2:])
+    {'launches': launches, 'kernel': kernel, 'pipe': pipe, 'stalls': stalls, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
