@@ -539,6 +539,7 @@ struct WgParams {
   // row-stacked mode of wgrad_tma_kernel (narrow 3x3 layers): stk_rz dout rows / stk_rz + 2 input rows of one clip
   // act as Ms = (virtual rows) * Cz / Nc = (virtual rows) * Cx "channels" of ONE 128-lane tile
   int stk, stk_rz, stk_groups, Cz, Cx;
+  int stk_nx, stk_xoff[2][8];   // input rows per tile and their offsets from the tile's first dout row, per CTA group
   int tap_of[9];         // (df + 1) * 3 + (dt + 1) -> index of that tap in the caller's table
 };
 
@@ -848,7 +849,7 @@ __device__ __forceinline__ void wg_epilogue(const WgParams& p, uint32_t tmem_bas
   const uint32_t lane_base = tmem_base + ((uint32_t)(lw * 32) << 16);
   const bool vec = p.w_sc == 1 && aq >= 16 && (((uintptr_t)dW) & 15) == 0 && p.w_tap_stride % 4 == 0 && p.w_sn % 4 == 0;
   if (vec) {
-    // stacked: block (dout row rzv, input row rx) is the tap df = rx - 1 - rzv
+    // stacked: block (dout row rzv, input row rxv) is the tap df = xoff[group][rxv] - rzv
     const int rzv = p.stk ? n / p.Cz : 0, co = p.stk ? n % p.Cz : n;
     const bool row_ok = m < p.Ms && (!p.stk || rzv < p.stk_rz);
     for (int j = 0; j < ntap; ++j) {
@@ -864,7 +865,9 @@ __device__ __forceinline__ void wg_epilogue(const WgParams& p, uint32_t tmem_bas
           if (v[0][k] == 0.f && v[1][k] == 0.f && v[2][k] == 0.f && v[3][k] == 0.f) continue;
           const int c = 4 * (cb + k);
           if (p.stk) {
-            const int ddf = c / p.Cx - 1 - rzv;
+            const int rxv = c / p.Cx;
+            if (rxv >= p.stk_nx) continue;
+            const int ddf = p.stk_xoff[g][rxv] - rzv;
             if (ddf < -1 || ddf > 1) continue;
             red_add_v4(dW + (long long)p.tap_of[(ddf + 1) * 3 + dt + 1] * p.w_tap_stride + (long long)co * p.w_sn + c % p.Cx,
                        v[0][k], v[1][k], v[2][k], v[3][k]);
@@ -988,9 +991,9 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
       const int f_src = fo + df;
       const bool f_ok = p.stk || (f_src >= 0 && f_src < p.F_in);
       if (!f_ok && !do_bias) continue;
-      // stacked: dout rows fo * rz + [0, rz), input rows fo * rz - 1 + [0, rz + 2); the others read as zero
+      // stacked: dout rows fo * rz + [0, rz), input rows fo * rz + xoff[group][0 .. nx); the others read as zero
       const bool z_row_ok = !p.stk || (zrow_v < p.stk_rz && fo * p.stk_rz + zrow_v < p.F_out);
-      const bool a_row_ok = !p.stk || (arow_v < p.stk_rz + 2 && (unsigned)(fo * p.stk_rz - 1 + arow_v) < (unsigned)p.F_in);
+      const bool a_row_ok = !p.stk || (arow_v < p.stk_nx && (unsigned)(fo * p.stk_rz + p.stk_xoff[g][arow_v]) < (unsigned)p.F_in);
       const int len_b = seq_len ? min(__ldg(seq_len + b), p.T) : p.T;
       const int len_out = p.mask_out ? len_b : p.T;
       const int t_end = min(p.T, (tb + 1) * WG_TB);
@@ -1141,7 +1144,8 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
           const uint32_t ez = p.out_bf16 ? 2u : 4u, ea = p.in_bf16 ? 2u : 4u;
           const int f0 = fo * p.stk_rz;
           int nzr = p.F_out - f0; if (nzr > p.stk_rz) nzr = p.stk_rz;
-          const int a_lo = f0 - 1 < 0 ? 0 : f0 - 1, a_hi = f0 + p.stk_rz < p.F_in - 1 ? f0 + p.stk_rz : p.F_in - 1;
+          int na = 0;                                                    // input rows of this tile inside the map
+          for (int v = 0; v < p.stk_nx; ++v) na += (unsigned)(f0 + p.stk_xoff[g][v]) < (unsigned)p.F_in;
           for (int t0 = tb * WG_TB; t0 < t_end; t0 += WG_KR, ++it) {
             const int rs = it % raw_stages;
             mbar_wait(&ctl->raw_empty[rs], ((it / raw_stages) & 1) ^ 1);
@@ -1149,15 +1153,18 @@ wgrad_tma_kernel(WgParams p, const __grid_constant__ CUtensorMap tm_z, const __g
             const int nz = min(WG_KR, p.T - t0);
             const int ts = t0 - 1 < 0 ? 0 : t0 - 1, te = min(t0 + WG_KR + 1, p.T);
             const uint32_t zb = (uint32_t)(nz * p.Cz) * ez, ab = (uint32_t)((te - ts) * p.Cx) * ea;
-            mbar_expect_tx(&ctl->raw_full[rs], zb * (uint32_t)nzr + ab * (uint32_t)(a_hi - a_lo + 1));
+            mbar_expect_tx(&ctl->raw_full[rs], zb * (uint32_t)nzr + ab * (uint32_t)na);
             for (int r = 0; r < nzr; ++r)
               bulk_g2s(dst + (uint32_t)(r * WG_KR * p.Cz) * ez,
                        reinterpret_cast<const uint8_t*>(dout) + (((size_t)b * p.F_out + f0 + r) * p.T + t0) * p.Cz * ez,
                        zb, &ctl->raw_full[rs]);
-            for (int f = a_lo; f <= a_hi; ++f)
-              bulk_g2s(dst + RAW_Z + (uint32_t)(((f - f0 + 1) * WG_RAW_AROWS + ts - (t0 - 1)) * p.Cx) * ea,
+            for (int v = 0; v < p.stk_nx; ++v) {
+              const int f = f0 + p.stk_xoff[g][v];
+              if ((unsigned)f >= (unsigned)p.F_in) continue;
+              bulk_g2s(dst + RAW_Z + (uint32_t)((v * WG_RAW_AROWS + ts - (t0 - 1)) * p.Cx) * ea,
                        reinterpret_cast<const uint8_t*>(in_raw) + (((size_t)b * p.F_in + f) * p.T + ts) * p.Cx * ea,
                        ab, &ctl->raw_full[rs]);
+            }
           }
           continue;
         }
@@ -1550,11 +1557,15 @@ int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, c
   static const int use_stack = getenv("PBSED_WG_STACK") ? atoi(getenv("PBSED_WG_STACK")) : 1;
   if (!use_stack || (d->precision != 1 && d->precision != 3)) return 0;
   if (d->ntaps != 9 || d->F_in != d->F_out || d->per_f) return 0;
-  int rz, ms, nc;
+  int rz, ms, nc, pair = 0;
   if (d->Cout == 16 && d->Cin == 16)      { rz = 6; ms = 128; nc = 128; }
   else if (d->Cout == 32 && d->Cin == 16) { rz = 4; ms = 128; nc = 128; }
   else if (d->Cout == 32 && d->Cin == 32) { rz = 2; ms = 64;  nc = 128; }
   else if (d->Cout == 64 && d->Cin == 32) { rz = 2; ms = 128; nc = 128; }
+  // 64 -> 64: two dout rows x TWO input rows per tile (four would need 768 TMEM columns), two CTA groups: rows
+  // {f, f+1} x {f, f+1} (all four blocks are taps) and {f, f+1} x {f-1, f+2} (two of four): 8 blocks computed for the 6
+  // needed, where a tile per (row, df) computes 128 x 64 with half the lanes empty
+  else if (d->Cout == 64 && d->Cin == 64 && (!getenv("PBSED_WG_PAIR") || atoi(getenv("PBSED_WG_PAIR")))) { rz = 2; ms = 128; nc = 128; pair = 1; }
   else return 0;
   if ((d->in_stride > 0 && d->in_stride != d->Cin) || (d->out_stride > 0 && d->out_stride != d->Cout)) return 0;
   if ((((uintptr_t)in | (uintptr_t)dout | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return 0;
@@ -1572,8 +1583,18 @@ int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, c
   p.single = d->precision == 3;
   p.in_bf16 = d->in_dtype == PBSED_BF16; p.out_bf16 = d->out_dtype == PBSED_BF16;
   p.Ms = ms; p.Nc = nc; p.m_slices = 1; p.c_slices = 1;
-  p.ngroups = 1; p.g_df[0] = 0; p.g_n[0] = 3;
-  for (int j = 0; j < 3; ++j) { p.g_tap[0][j] = j; p.g_dt[0][j] = j - 1; }
+  p.ngroups = pair ? 2 : 1;
+  for (int g = 0; g < p.ngroups; ++g) {
+    p.g_df[g] = 0; p.g_n[g] = 3;
+    for (int j = 0; j < 3; ++j) { p.g_tap[g][j] = j; p.g_dt[g][j] = j - 1; }
+  }
+  if (pair) {
+    p.stk_nx = 2;
+    p.stk_xoff[0][0] = 0; p.stk_xoff[0][1] = 1; p.stk_xoff[1][0] = -1; p.stk_xoff[1][1] = 2;
+  } else {
+    p.stk_nx = rz + 2;
+    for (int v = 0; v < p.stk_nx; ++v) p.stk_xoff[0][v] = v - 1;
+  }
   p.stk = 1; p.stk_rz = rz; p.stk_groups = cdiv(d->F_out, rz); p.Cz = d->Cout; p.Cx = d->Cin;
   if ((long long)p.B * p.stk_groups * cdiv(p.T, WG_TB) > 0x7fffffffLL) return 0;
   const size_t stage = 2 * (size_t)WG_ZCH * 128 * 16 + 2 * (size_t)WG_ACH * p.Nc * 16;
@@ -1583,7 +1604,7 @@ int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, c
   if (raw_stages > WG_RAW_MAX) raw_stages = WG_RAW_MAX;
   if (raw_stages < 2) return 0;
   const int units = p.B * p.stk_groups * cdiv(p.T, WG_TB);
-  int rs = 148;
+  int rs = 148 / p.ngroups;
   if (rs > units) rs = units;
   p.row_splits = rs;
   const size_t smem = WG_STAGES * stage + (size_t)raw_stages * raw + sizeof(WgTmaCtl) + 128;
@@ -1591,7 +1612,7 @@ int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, c
   if (e != cudaSuccess) return (int)e;
   CUtensorMap none = {};
   pbsed_note_kernel("wgrad_tma_kernel");                  // (same kernel, row-stacked mode: one name, as ncu lists it)
-  wgrad_tma_kernel<<<dim3(rs, 1, 1), WT_CONV + 64, smem, st>>>(p, none, none, raw_stages, in, scale, shift, seq_len, dout, dW, dbias);
+  wgrad_tma_kernel<<<dim3(rs, p.ngroups, 1), WT_CONV + 64, smem, st>>>(p, none, none, raw_stages, in, scale, shift, seq_len, dout, dW, dbias);
   *handled = 1;
   return pbsed_after_launch();
 }

@@ -91,6 +91,7 @@ def test_tc_dgrad_with_relu_mask_epilogue(built_lib):
     (3, 13, 45, 16, 16, TAPS_3x3, False),      # narrow layers: row-stacked tiles with a ragged last row group
     (2, 7, 100, 16, 32, TAPS_3x3, True),
     (3, 5, 70, 32, 32, TAPS_3x3, True),
+    (2, 5, 90, 64, 64, TAPS_3x3, True),        # two dout rows x two input rows per tile, two CTA groups
     (2, 4, 500, 32, 64, TAPS_3x3, True),
     (2, 2, 300, 128, 256, TAPS_3x3, True),
     (3, 1, 500, 256, 768, TAPS_1x1, False),
