@@ -216,16 +216,19 @@ def kernel_breakdown(model, opt, batch, train, _lib):
     main kernel (``pbsed_last_kernel``)."""
     import torch
     from pb_sed_b200 import ops
-    # the un-graphed drop-in step (what a stock trainer loop runs): 1 warm-up (allocator), then 3 timed
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the un-graphed drop-in step (what a stock trainer loop runs): 1 warm-up (allocator), then the MEDIAN of 5 timed
+    # steps -- the eager step is bound by host issue time, and one descheduled Python thread tripled a 3-step mean
     train.train_step(model, opt, batch)
     torch.cuda.synchronize()
-    t0.record()
-    for _ in range(3):
+    times = []
+    for _ in range(5):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
         train.train_step(model, opt, batch)
-    t1.record()
-    torch.cuda.synchronize()
-    eager_ms = t0.elapsed_time(t1) / 3.
+        t1.record()
+        torch.cuda.synchronize()
+        times.append(t0.elapsed_time(t1))
+    eager_ms = sorted(times)[len(times) // 2]
     ops.enable_wgrad_stream(False)          # isolate the per-call timings (no concurrent side-stream kernels)
     sink = []
     _lib.profile_sink = sink
