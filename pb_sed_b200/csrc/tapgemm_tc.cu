@@ -1554,7 +1554,8 @@ int tapgemm_wgrad_stack_dispatch(const pbsed_tapgemm_desc* d, const float* in, c
                                  const float* shift, const int* seq_len, const float* dout,
                                  int mask_out, float* dW, float* dbias, cudaStream_t st, int* handled) {
   *handled = 0;
-  static const int use_stack = getenv("PBSED_WG_STACK") ? atoi(getenv("PBSED_WG_STACK")) : 1;
+  const char* stack_env = getenv("PBSED_WG_STACK");              // read per call: the tests switch it to reach the fallback
+  const int use_stack = stack_env ? atoi(stack_env) : 1;
   if (!use_stack || (d->precision != 1 && d->precision != 3)) return 0;
   if (d->ntaps != 9 || d->F_in != d->F_out || d->per_f) return 0;
   int rz, ms, nc, pair = 0;

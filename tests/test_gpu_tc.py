@@ -119,6 +119,34 @@ def test_tc_wgrad_matches_ffma(built_lib, B, F, T, Cin, Cout, taps, relu):
     assert float(res[0][0].abs().max()) > 0
 
 
+@pytest.mark.parametrize('B,F,T,Cin,Cout,relu', [
+    (2, 3, 37, 16, 16, True), (3, 13, 45, 16, 16, False), (2, 7, 100, 16, 32, True), (3, 5, 70, 32, 32, True),
+    (2, 4, 500, 32, 64, True),
+])
+def test_narrow_wgrad_fallback_walk_kernel_matches_ffma(built_lib, monkeypatch, B, F, T, Cin, Cout, relu):
+    """the frequency-walking mma.sync kernel behind the row-stacked tcgen05 tiles (PBSED_WG_STACK=0, read per call):
+    same ragged cases, same bar against the exact-fp32 kernels; the last kernel name proves which one ran."""
+    from pb_sed_b200 import ops, _lib
+    monkeypatch.setenv('PBSED_WG_STACK', '0')
+    torch.manual_seed(Cin + Cout + T)
+    x = torch.randn(B, F, T, Cin, device=DEV)
+    dz = torch.randn(B, F, T, Cout, device=DEV)
+    scale = torch.rand(Cin, device=DEV) + .5
+    shift = torch.randn(Cin, device=DEV) * .3
+    sl = np.minimum(np.array([T, max(T - 3, 1), max(T // 2, 1)][:B]), T)
+    seq = ops.SeqLen.make(sl, B, T, DEV)
+    res = []
+    for prec in (0, 1):
+        desc = ops.make_desc(B, F, F, T, Cin, Cout, TAPS_3x3, relu=relu, precision=prec)
+        dW = torch.zeros(9, Cout, Cin, device=DEV)
+        db = torch.zeros(Cout, device=DEV)
+        ops.tapgemm_wgrad(x, dz, desc, dW, db, scale if relu else None, shift if relu else None, seq, mask_out=True)
+        res.append((dW, db))
+    assert _lib.load().pbsed_last_kernel().decode() == 'wgrad_walk_kernel'
+    assert reldiff(res[1][0], res[0][0]) < 5e-5
+    assert reldiff(res[1][1], res[0][1]) < 5e-5
+
+
 def test_tc_wgrad_flatten_and_strided_input(built_lib):
     """per-(f,c) affine with 8 frequency taps; and the GRU W_hh gradient reading one direction's half of a
     (B,T,2H) map (in_stride = 2H)."""
