@@ -1624,8 +1624,8 @@ int tapgemm_wgrad_tc_dispatch(const pbsed_tapgemm_desc* d, const float* in, cons
   *handled = 0;
   if ((d->precision != 1 && d->precision != 3) || !tc_eligible(d)) return 0;
   if (d->Cin > NSLICE && d->Cin % NSLICE) return 0;
-  // measured crossover (B200, B=32): with <= 32 channels on a side the 128-lane MMA is mostly padding
-  // and the FFMA kernel wins; see DESIGN.md
+  // a tile per (row, df group): with <= 32 channels on a side the 128-lane MMA is mostly padding -- the 3x3 layers of
+  // that width take the row-stacked tiles (tapgemm_wgrad_stack_dispatch, tried first), other shapes the narrow kernels
   if (!(d->Cin >= 64 || (d->Cin >= 32 && d->Cout >= 128))) return 0;
   if ((((uintptr_t)in | (uintptr_t)dout | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return 0;
   WgParams p = {};

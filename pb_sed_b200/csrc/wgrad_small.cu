@@ -1,12 +1,13 @@
-// wgrad_small.cu -- weight gradient of the narrow 3x3 conv layers (16 / 32 channels on the input side).
+// wgrad_small.cu -- weight gradient of the narrow 3x3 conv layers (16 / 32 channels on the input side) in EXACT fp32
+// (precision 0: the reference the tensor-core kernels are tested against, and the 'fp32' mode of the library).
 //
 // Reference: backward of padertorch CNN2d layers 1-4 (pb_sed/experiments/weak_label_crnn/training.py:
 // 158-169: channels 16,16,32,32,64).  These layers are HBM streams (each map is 131 MB at B = 32) with
-// only 2.3k-18k MACs per frame, far below what fills a 128-lane MMA, and the generic kernel re-reads
-// both maps once per tap.  Here ONE CTA forms all nine taps from a single staged tile: dout tile
-// (64 frames x Cout) + three input strips (f-1, f, f+1; 66 frames x Cin; norm + ReLU + mask applied
-// while staging), each thread keeps NPT x CPT x 9 accumulators in registers across all its work units
-// and slides a 3-frame window over the input strip, so shared memory is read ~once per 6 FMAs.
+// only 2.3k-18k MACs per frame, and the generic FFMA kernel re-reads both maps once per tap.  Here ONE CTA forms all
+// nine taps from a single staged tile: dout tile (64 frames x Cout) + three input strips (f-1, f, f+1; 66 frames x
+// Cin; norm + ReLU + mask applied while staging), each thread keeps NPT x CPT x 9 accumulators in registers across
+// all its work units and slides a 3-frame window over the input strip, so shared memory is read ~once per 6 FMAs.
+// (In the tensor-core modes these layers run as row-stacked tcgen05 tiles, tapgemm_tc.cu.)
 #include "common.cuh"
 
 struct WsParams {
