@@ -233,3 +233,17 @@ def test_augmentation_samplers_follow_the_configured_distributions():
     assert stats.chisquare(counts).pvalue > 1e-3
     short = NormalizedLogMelExtractor._masks(1, torch.full((n,), 40.), 70, .2, 'cpu').numpy()[:, 0]
     assert short[:, 1].max() == 8 and (short.sum(-1) <= 40).all()      # min(70, floor(.2 * 40)) = 8
+
+
+def test_bench_counts_only_valid_taps_as_algorithmic_flops():
+    """bench.py's roofline numerator (round-1 review: the transposed flatten data gradient F 1 -> 8 was credited all 8
+    taps per output row although exactly ONE source row exists): 2 * Cin * Cout per VALID (output row, tap) pair."""
+    import ctypes
+    import bench
+    from pb_sed_b200 import ops
+    taps3 = [(a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)]
+    d = ops.make_desc(2, 4, 4, 10, 16, 32, taps3, precision=1)
+    pairs = (3 + 4 + 3) * (9 + 10 + 9)                       # rows with a source row x frames with a source frame
+    assert bench.tapgemm_flops((ctypes.byref(d),)) == 2. * 2 * pairs * 16 * 32
+    flat = ops.make_desc(2, 1, 8, 10, 256, 256, [(-f, 0) for f in range(8)], precision=1)
+    assert bench.tapgemm_flops((ctypes.byref(flat),)) == 2. * 2 * 8 * 10 * 256 * 256      # one tap per output row
