@@ -247,3 +247,22 @@ def test_bench_counts_only_valid_taps_as_algorithmic_flops():
     assert bench.tapgemm_flops((ctypes.byref(d),)) == 2. * 2 * pairs * 16 * 32
     flat = ops.make_desc(2, 1, 8, 10, 256, 256, [(-f, 0) for f in range(8)], precision=1)
     assert bench.tapgemm_flops((ctypes.byref(flat),)) == 2. * 2 * 8 * 10 * 256 * 256      # one tap per output row
+
+
+def test_traffic_table_uses_the_kernel_names_the_library_reports():
+    """bench.py fills ``roofline.traffic`` by looking the dominant kernel's ``pbsed_last_kernel()`` name up in
+    profiles/traffic.json (measured DRAM bytes per launch, tools/ncu_summary.py traffic): the tensor-core kernels that
+    can dominate a step must be present under exactly the names the sources pass to ``pbsed_note_kernel``."""
+    import glob
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    noted = set()
+    for path in glob.glob(os.path.join(root, 'pb_sed_b200', 'csrc', '*.cu')):
+        noted.update(re.findall(r'"((?:tapgemm|wgrad|conv_cin1)[a-z0-9_]*(?:<[0-9,]+>)?)"', open(path).read()))
+    table = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
+    for name in ('wgrad_tma_kernel', 'tapgemm_tc_kernel<2,2,256>', 'tapgemm_tc_kernel<2,4,256>', 'tapgemm_tc_kernel<1,4,256>',
+                 'tapgemm_fw_kernel'):
+        assert name in noted, name
+        assert table[name]['bytes_per_launch'] > 1e6 and table[name]['launches_captured'] >= 1, name
